@@ -1,0 +1,360 @@
+"""Graph containers of the LF-MMI chain loss: `ChainGraph` / `ChainGraphBatch`.
+
+Drop-in for the reference's `pychain/graph.py` (ChainGraph :23-70,
+ChainGraphBatch :73-194): same class names, constructor arguments, attribute
+names, dtypes and tensor layouts, so code written
+against `pychain.graph` keeps working.  Differences, all behind that surface:
+
+* The reference can only build a graph from an OpenFst object through its
+  `simplefst` binding (`openfst_binding/src/fstext.cc`).  OpenFst is not a
+  dependency here: `Fst` below is a tiny arc-list container (also readable from
+  OpenFst/AT&T text format) and the CSR construction (`fstext.cc:19-117`) and
+  the leaky-HMM occupancy estimate (`fstext.cc:120-171`) are restated over
+  numpy arrays.  If `simplefst` *is* importable a real `StdVectorFst` is
+  accepted too and routed through it, exactly as the reference does.
+* `ChainGraphBatch(graph, B)` (one shared graph, the denominator case) does not
+  materialise B copies (`graph.py:101-120` uses `.repeat`): the batch tensors
+  are stride-0 `expand` views of the single graph, i.e. the `[B,K,3]` layout
+  contract is kept but costs O(1) memory, and the engine recognises the
+  stride-0 batch dimension and runs its shared-graph kernels.
+"""
+from __future__ import annotations
+
+import math
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+try:  # optional: the reference's OpenFst binding
+    import simplefst  # type: ignore
+except Exception:  # pragma: no cover - not available in this image
+    simplefst = None
+
+__all__ = ["Fst", "ChainGraph", "ChainGraphBatch"]
+
+
+class Fst(object):
+    """Minimal epsilon-free weighted acceptor in the tropical/log semiring.
+
+    Arc weights and final weights are stored as *log-probabilities*
+    (= minus the OpenFst weight, as `fstext.cc:38,45` negates them).  `pdf` is
+    `ilabel - 1` (`fstext.cc:41`).  Arc order within a state is insertion order
+    (what `fst::ArcIterator` yields); states are 0..num_states-1.
+    """
+
+    def __init__(self, num_states: int, start: int, src, dst, pdf, log_weight, final_log_weight=None):
+        self._num_states = int(num_states)
+        self._start = int(start)
+        self.src = np.asarray(src, dtype=np.int64).reshape(-1)
+        self.dst = np.asarray(dst, dtype=np.int64).reshape(-1)
+        self.pdf = np.asarray(pdf, dtype=np.int64).reshape(-1)
+        self.log_weight = np.asarray(log_weight, dtype=np.float32).reshape(-1)
+        if final_log_weight is None:
+            final_log_weight = np.full(self._num_states, -np.inf, dtype=np.float32)
+        self.final_log_weight = np.asarray(final_log_weight, dtype=np.float32).reshape(-1)
+        n = self.src.shape[0]
+        if not (self.dst.shape[0] == n and self.pdf.shape[0] == n and self.log_weight.shape[0] == n):
+            raise ValueError("Fst: src/dst/pdf/log_weight must have the same length")
+        if self.final_log_weight.shape[0] != self._num_states:
+            raise ValueError("Fst: final_log_weight must have num_states entries")
+        if n and (self.src.min() < 0 or self.src.max() >= self._num_states or
+                  self.dst.min() < 0 or self.dst.max() >= self._num_states):
+            raise ValueError("Fst: arc endpoint out of range")
+        if n and self.pdf.min() < 0:
+            raise ValueError("Fst: negative pdf id (epsilon input labels are not allowed, fstext.cc:41-42)")
+        # canonical FST iteration order: by source state, stable (insertion order within a state)
+        order = np.argsort(self.src, kind="stable")
+        self.src, self.dst, self.pdf, self.log_weight = (
+            self.src[order], self.dst[order], self.pdf[order], self.log_weight[order])
+
+    # -- the part of the simplefst.StdVectorFst API that graph.py uses ----------
+    def num_states(self) -> int:
+        return self._num_states
+
+    def start_state(self) -> int:
+        return self._start
+
+    @property
+    def num_arcs(self) -> int:
+        return int(self.src.shape[0])
+
+    @classmethod
+    def from_text(cls, lines: Iterable[str]) -> "Fst":
+        """Parse OpenFst text format (`fstprint`): `src dst ilabel olabel [w]`
+        arc lines and `state [w]` final lines; start = source of the first line.
+        Weights are tropical/log costs, so log-prob = -w.  pdf = ilabel - 1."""
+        src, dst, pdf, lw = [], [], [], []
+        finals = {}
+        start = None
+        nstates = 0
+        for line in lines:
+            f = line.split()
+            if not f:
+                continue
+            if start is None:
+                start = int(f[0])
+            if len(f) >= 4:
+                s, d, il = int(f[0]), int(f[1]), int(f[2])
+                w = float(f[4]) if len(f) >= 5 else 0.0
+                src.append(s), dst.append(d), pdf.append(il - 1), lw.append(-w)
+                nstates = max(nstates, s + 1, d + 1)
+            else:
+                s = int(f[0])
+                w = float(f[1]) if len(f) >= 2 else 0.0
+                finals[s] = -w
+                nstates = max(nstates, s + 1)
+        fin = np.full(nstates, -np.inf, dtype=np.float32)
+        for s, w in finals.items():
+            fin[s] = w
+        return cls(nstates, start or 0, src, dst, pdf, lw, fin)
+
+    # -- fstext.cc:19-117 restated ---------------------------------------------
+    def to_tensors(self, log_domain: bool = False):
+        """CSR by source and CSR by destination, as `FstToTensor` emits them.
+        Returns the same 7-tuple in the same order (`fstext.cc:109-116`)."""
+        S, K = self._num_states, self.num_arcs
+        fwd = np.stack([self.src, self.dst, self.pdf], axis=1).astype(np.int32).reshape(K, 3)
+        out_deg = np.bincount(self.src, minlength=S)
+        fwd_end = np.cumsum(out_deg)
+        fwd_idx = np.stack([fwd_end - out_deg, fwd_end], axis=1).astype(np.int32)
+        # transitions_in_tup[dst] is appended while iterating states/arcs in
+        # forward order (fstext.cc:36-47) => stable sort of the forward list by dst
+        border = np.argsort(self.dst, kind="stable")
+        bwd = fwd[border]
+        in_deg = np.bincount(self.dst, minlength=S)
+        bwd_end = np.cumsum(in_deg)
+        bwd_idx = np.stack([bwd_end - in_deg, bwd_end], axis=1).astype(np.int32)
+        fwd_p = torch.from_numpy(self.log_weight.copy())
+        bwd_p = torch.from_numpy(self.log_weight[border].copy())
+        fin = torch.from_numpy(self.final_log_weight.copy())
+        if not log_domain:  # fstext.cc:89-90, 101-102, 106-107
+            fwd_p.exp_(), bwd_p.exp_(), fin.exp_()
+        return (torch.from_numpy(fwd.copy()), fwd_p, torch.from_numpy(fwd_idx),
+                torch.from_numpy(bwd.copy()), bwd_p, torch.from_numpy(bwd_idx), fin)
+
+    # -- fstext.cc:120-171 restated --------------------------------------------
+    def leaky_probs(self, num_iters: int = 100) -> torch.Tensor:
+        """Average state occupancy over `num_iters` steps of the per-state
+        normalised HMM started in the start state (float64, returned float32)."""
+        S = self._num_states
+        w = np.exp(self.log_weight.astype(np.float64))
+        tot = np.exp(self.final_log_weight.astype(np.float64)) + np.bincount(self.src, weights=w, minlength=S)
+        with np.errstate(divide="ignore"):
+            nf = 1.0 / tot
+        cur = np.zeros(S, dtype=np.float64)
+        cur[self._start] = 1.0
+        avg = np.zeros(S, dtype=np.float64)
+        for _ in range(num_iters):
+            avg += cur * (1.0 / num_iters)
+            nxt = np.bincount(self.dst, weights=(cur * nf)[self.src] * w, minlength=S)
+            cur = nxt * (1.0 / nxt.sum())
+        return torch.from_numpy(avg.astype(np.float32))
+
+
+def _is_simplefst(fst) -> bool:
+    return simplefst is not None and isinstance(fst, simplefst.StdVectorFst)
+
+
+class ChainGraph(object):
+    """One numerator or denominator graph (reference `graph.py:23-70`).
+
+    Attributes (identical to the reference): `num_states`, `num_transitions`,
+    `log_domain`, `is_empty`, `start_state`, `forward_transitions [K,3] i32`,
+    `forward_transition_indices [S,2] i32`, `forward_transition_probs [K] f32`,
+    the three `backward_*` twins, `final_probs [S]`, `initial_probs [S]`,
+    `leaky_probs [S]` (None in the log domain).
+    """
+
+    def __init__(self, fst, initial_mode="fst", final_mode="fst", log_domain=False):
+        self.num_states = fst.num_states()
+        assert initial_mode in ["fst", "leaky"]
+        assert final_mode in ["fst", "ones"]
+        self.log_domain = log_domain
+        if _is_simplefst(fst):  # the reference's own route (graph.py:36-44)
+            tensors = simplefst.StdVectorFst.fst_to_tensor(fst, log_domain)
+            start = simplefst.StdVectorFst.start_state(fst)
+            leaky_fn = lambda: simplefst.StdVectorFst.set_leaky_probs(fst)  # noqa: E731
+        elif isinstance(fst, Fst):
+            tensors = fst.to_tensors(log_domain)
+            start = fst.start_state()
+            leaky_fn = fst.leaky_probs
+        else:
+            raise TypeError("ChainGraph expects a pychain_b200.Fst (or a simplefst.StdVectorFst), got {}".format(type(fst)))
+        (
+            self.forward_transitions,
+            self.forward_transition_probs,
+            self.forward_transition_indices,
+            self.backward_transitions,
+            self.backward_transition_probs,
+            self.backward_transition_indices,
+            self.final_probs,
+        ) = tensors
+
+        self.num_transitions = self.forward_transitions.size(0)
+        self.is_empty = (self.num_transitions == 0)
+        self.start_state = start
+
+        probs_type = self.forward_transition_probs.dtype
+
+        if not self.is_empty:
+            if log_domain:
+                self.leaky_probs = None  # no leaky hmm if in log domain
+                assert initial_mode == "fst", "'leaky' mode is incompatible with log domain"
+                self.initial_probs = torch.full([self.num_states], float("-inf"), dtype=probs_type)
+                self.initial_probs[self.start_state] = 0.0
+                if final_mode == "ones":
+                    self.final_probs.fill_(0.0)
+            else:
+                self.leaky_probs = leaky_fn()
+                if initial_mode == "fst":
+                    self.initial_probs = torch.zeros([self.num_states], dtype=probs_type)
+                    self.initial_probs[self.start_state] = 1.0
+                else:
+                    self.initial_probs = self.leaky_probs.clone()
+                if final_mode == "ones":
+                    self.final_probs.fill_(1.0)
+        else:
+            raise Exception("An empty graph encountered!")
+        self._engine_cache = {}  # per-device prepared (packed, device-resident) views, filled by the engine
+
+    _GRAPH_FIELDS = (
+        "forward_transitions", "forward_transition_indices", "forward_transition_probs",
+        "backward_transitions", "backward_transition_indices", "backward_transition_probs",
+        "final_probs", "initial_probs", "leaky_probs",
+    )
+
+
+class ChainGraphBatch(object):
+    """A batch of graphs in the reference's padded `[B, ...]` layout
+    (`graph.py:73-194`).  Same constructor, same attributes, same `reorder`."""
+
+    def __init__(self, graphs, batch_size=None, max_num_transitions=None, max_num_states=None):
+        self.shared_graph = None  # the single ChainGraph when all B rows are the same graph
+        if isinstance(graphs, ChainGraph):
+            if not batch_size:
+                raise ValueError("batch size should be specified to expand a single graph")
+            self.batch_size = batch_size
+            self.initialized_by_one(graphs)
+        elif isinstance(graphs, (list, ChainGraph)):
+            if not max_num_transitions:
+                raise ValueError(
+                    "max_num_transitions should be specified if given a "
+                    "a list of ChainGraph objects to initialize from"
+                )
+            if not max_num_states:
+                raise ValueError(
+                    "max_num_states should be specified if given a "
+                    "a list of ChainGraph objects to initialize from"
+                )
+            self.batch_size = len(graphs)
+            self.initialized_by_list(graphs, max_num_transitions, max_num_states)
+        else:
+            raise ValueError(
+                "ChainGraphBatch should be either initialized by a "
+                "single ChainGraph object or a list of ChainGraph objects "
+                "but given {}".format(type(graphs))
+            )
+
+    def initialized_by_one(self, graph):
+        """Reference `graph.py:101-120` repeats the graph B times; here every
+        batch tensor is a stride-0 view of the one graph (same shapes)."""
+        self.log_domain = graph.log_domain
+        self.shared_graph = graph
+        B = self.batch_size
+
+        def ex(t):
+            return t.unsqueeze(0).expand(B, *t.shape)
+
+        self.forward_transitions = ex(graph.forward_transitions)
+        self.forward_transition_indices = ex(graph.forward_transition_indices)
+        self.forward_transition_probs = ex(graph.forward_transition_probs)
+        self.backward_transitions = ex(graph.backward_transitions)
+        self.backward_transition_indices = ex(graph.backward_transition_indices)
+        self.backward_transition_probs = ex(graph.backward_transition_probs)
+        self.num_states = graph.num_states
+        self.num_transitions = graph.num_transitions
+        self.final_probs = ex(graph.final_probs)
+        self.leaky_probs = ex(graph.leaky_probs) if not self.log_domain else None
+        self.initial_probs = ex(graph.initial_probs)
+        self.start_state = graph.start_state * torch.ones(B, dtype=torch.long)
+
+    def initialized_by_list(self, graphs, max_num_transitions, max_num_states):
+        """Zero / -inf padded stack, as reference `graph.py:122-175`."""
+        transition_type = graphs[0].forward_transitions.dtype
+        probs_type = graphs[0].forward_transition_probs.dtype
+        self.log_domain = graphs[0].log_domain
+        self.num_states = max_num_states
+        self.num_transitions = max_num_transitions
+        B = self.batch_size
+        self.forward_transitions = torch.zeros([B, max_num_transitions, 3], dtype=transition_type)
+        self.forward_transition_indices = torch.zeros([B, max_num_states, 2], dtype=transition_type)
+        self.forward_transition_probs = torch.zeros([B, max_num_transitions], dtype=probs_type)
+        self.backward_transitions = torch.zeros([B, max_num_transitions, 3], dtype=transition_type)
+        self.backward_transition_indices = torch.zeros([B, max_num_states, 2], dtype=transition_type)
+        self.backward_transition_probs = torch.zeros([B, max_num_transitions], dtype=probs_type)
+        if self.log_domain:
+            self.leaky_probs = None  # no leaky hmm if in log domain
+            self.initial_probs = torch.full([B, max_num_states], float("-inf"), dtype=probs_type)
+            self.final_probs = torch.full([B, max_num_states], float("-inf"), dtype=probs_type)
+        else:
+            self.leaky_probs = torch.zeros([B, max_num_states], dtype=probs_type)
+            self.initial_probs = torch.zeros([B, max_num_states], dtype=probs_type)
+            self.final_probs = torch.zeros([B, max_num_states], dtype=probs_type)
+        self.start_state = torch.zeros([B], dtype=torch.long)
+
+        for i, graph in enumerate(graphs):
+            nt, ns = graph.num_transitions, graph.num_states
+            if nt > max_num_transitions or ns > max_num_states:
+                raise ValueError("graph {} ({} states, {} transitions) exceeds the batch maxima".format(i, ns, nt))
+            self.forward_transitions[i, :nt, :].copy_(graph.forward_transitions)
+            self.forward_transition_indices[i, :ns, :].copy_(graph.forward_transition_indices)
+            self.forward_transition_probs[i, :nt].copy_(graph.forward_transition_probs)
+            self.backward_transitions[i, :nt, :].copy_(graph.backward_transitions)
+            self.backward_transition_indices[i, :ns, :].copy_(graph.backward_transition_indices)
+            self.backward_transition_probs[i, :nt].copy_(graph.backward_transition_probs)
+            if self.leaky_probs is not None:
+                self.leaky_probs[i, :ns].copy_(graph.leaky_probs)
+            self.initial_probs[i, :ns].copy_(graph.initial_probs)
+            self.final_probs[i, :ns].copy_(graph.final_probs)
+            self.start_state[i] = graph.start_state
+
+    _BATCH_FIELDS = (
+        "forward_transitions", "forward_transition_indices", "forward_transition_probs",
+        "backward_transitions", "backward_transition_indices", "backward_transition_probs",
+        "leaky_probs", "initial_probs", "final_probs", "start_state",
+    )
+
+    def reorder(self, new_order):
+        """Reference `graph.py:177-194`.  For a shared graph every row is the
+        same graph, so the (stride-0) graph tensors are left untouched."""
+        if self.shared_graph is not None:
+            if new_order.numel() != self.batch_size:
+                self.batch_size = int(new_order.numel())
+                self.initialized_by_one(self.shared_graph)
+            return
+        for name in self._BATCH_FIELDS:
+            t = getattr(self, name)
+            if t is not None:
+                setattr(self, name, t.index_select(0, new_order.to(t.device)))
+
+    # -- conveniences that the reference does not have ---------------------------
+    def to(self, device):
+        """Move the batch tensors to `device` once, instead of the reference's
+        per-call `.cuda()` inside the extension (`chain-computation.cc:77-89`)."""
+        for name in self._BATCH_FIELDS:
+            t = getattr(self, name)
+            if t is not None:
+                setattr(self, name, t.to(device))
+        return self
+
+    def materialize(self):
+        """Contiguous `[B, ...]` copies (what the reference's `.repeat` makes);
+        needed only to hand a shared-graph batch to the *reference* extension,
+        whose CHECK_CONTIGUOUS (`pychain.cc:42-54`) rejects stride-0 views."""
+        for name in self._BATCH_FIELDS:
+            t = getattr(self, name)
+            if t is not None:
+                setattr(self, name, t.contiguous())
+        self.shared_graph = None
+        return self
