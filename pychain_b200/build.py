@@ -1,0 +1,56 @@
+"""Build libchain_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python -m pychain_b200.build [--force] [--verbose]
+
+The .so lands in pychain_b200/lib/ (git-ignored, shipped to the GPU box by
+gpurun).  No torch headers, no pybind: the library's interface is
+include/chain_b200.h and nothing else.
+"""
+import os
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "lib", "libchain_b200.so")
+SOURCES = ["generic.cu", "den_shared.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+    "-Xptxas", "-v",
+]
+
+
+def _sources():
+    return [os.path.join(CSRC, f) for f in SOURCES if os.path.isfile(os.path.join(CSRC, f))]
+
+
+def needs_build():
+    if not os.path.isfile(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = _sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(ROOT, "include", "chain_b200.h"))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB] + _sources()
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log = r.stdout + r.stderr
+    with open(os.path.join(PKG, "lib", "build.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + log)
+    if verbose or r.returncode != 0:
+        print(log)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed building libchain_b200.so")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv))

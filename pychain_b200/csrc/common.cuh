@@ -1,0 +1,87 @@
+// common.cuh -- shared device/host helpers of the chain_b200 engine (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "chain_b200.h"
+
+namespace chainb200 {
+
+constexpr float kClampLo = -30.0f;  // loss.py:30
+constexpr float kClampHi = 30.0f;
+constexpr size_t kAlign = 256;
+
+inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }
+
+// Per-thread launch counter (bench.py's gpu_launches).
+extern thread_local int g_launch_count;
+extern int g_verbose_level;
+
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) {
+      err = cudaSetDevice(device);
+      switched = (err == cudaSuccess);
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+// ---------------------------------------------------------------- device side
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum, result returned to every thread.  Fixed summation order
+// (lane tree, then warps 0..nw-1) => deterministic.  `scratch` needs >= 32 floats.
+// Contains two __syncthreads(): safe to call back to back with the same scratch.
+__device__ __forceinline__ float block_sum(float v, float *scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < nw; w++) t += scratch[w];
+  __syncthreads();
+  return t;
+}
+
+// log(sum_i exp(v_i)) over the block from per-thread (m, s) pairs with
+// s = sum exp(v - m); m = -inf means "no terms".  Result to every thread.
+__device__ __forceinline__ void lse_merge(float &m, float &s, float m2, float s2) {
+  const float M = fmaxf(m, m2);
+  if (M == -INFINITY) { m = M; s = 0.f; return; }
+  s = s * expf(m - M) + s2 * expf(m2 - M);
+  m = M;
+}
+__device__ __forceinline__ float block_lse(float m, float s, float *scratch /* >= 64 floats */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    lse_merge(m, s, m2, s2);
+  }
+  if (lane == 0) { scratch[2 * warp] = m; scratch[2 * warp + 1] = s; }
+  __syncthreads();
+  float M = -INFINITY, Sx = 0.f;
+  for (int w = 0; w < nw; w++) lse_merge(M, Sx, scratch[2 * w], scratch[2 * w + 1]);
+  __syncthreads();
+  return (M == -INFINITY) ? -INFINITY : M + logf(Sx);
+}
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+}  // namespace chainb200

@@ -1,0 +1,799 @@
+// den_shared.cu -- denominator forward-backward for ONE graph shared by the batch, sm_100a.
+//
+// This is the headline path: the reference runs it as ChainGraphBatch(den_graph, B)
+// (pychain/loss.py:99) -> pychain_C.forward_backward (pychain.cc:26-79) ->
+// ChainComputation::Forward/Backward (chain-computation.cc:196-207, 332-342), i.e. one
+// kernel + 3 ATen launches per frame and direction, a thread per (sequence, state) with the
+// sequence index as the SLOWEST memory dimension, and per-arc thresholded atomics for the
+// gradient (chain-kernels.cu:97-245).
+//
+// Design here:
+//  * persistent CTAs, each owning a GROUP of G (1, 2 or 4) utterances for the whole
+//    recursion; the G utterances are interleaved as the fastest dimension of every
+//    on-chip array (alpha[state][g], x[pdf][g]) so that one arc record fetched from L2 and
+//    one vector LDS per operand serve G arc-visits.
+//  * the graph is packed ONCE on the host (chain_b200_den_prepare) into three sliced-ELL
+//    ("SELL-32") views -- keyed by destination (alpha pass), by source (beta pass) and by
+//    pdf (gamma pass) -- rows sorted by degree, 32 rows per slice, records stored
+//    [slice][k][lane] as 8-byte {a:16 | b:16, weight:f32}: every warp-level record fetch is
+//    one coalesced 256-byte read, every lane owns one row and accumulates in registers.
+//    No atomics anywhere; summation order inside a row is the reference's CSR order.
+//  * alpha'(t) rows ([S][G] floats, contiguous) are spilled with coalesced 128-bit stores
+//    and brought back for the backward pass with one TMA bulk copy (cp.async.bulk +
+//    mbarrier) per frame; the frames of x are staged by TMA bulk copies one frame ahead and
+//    exp/clamp are applied while transposing them into the interleaved layout.
+//  * leaky-HMM mixing, per-frame renormalisation, total log-likelihood, the t=0 self-check
+//    and the zeroing of padded frames are all inside the one kernel.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+
+namespace chainb200 {
+
+constexpr uint32_t kBlobMagic = 0x42324348u;  // "HC2B"
+constexpr uint32_t kBlobVersion = 2;
+constexpr int DEN_NW = 16;
+constexpr int DEN_NT = DEN_NW * 32;
+
+struct BlobView {
+  int32_t n_rows, n_slices;
+  int64_t n_recs;
+  int64_t off_rows;         // int32 [n_slices*32]  row id per (slice, lane), -1 = padding lane
+  int64_t off_desc;         // int2  [n_slices]     {record offset, width}
+  int64_t off_warp_ptr;     // int32 [nwarps+1]
+  int64_t off_warp_slices;  // int32 [n_slices]     slice ids grouped by warp
+  int64_t off_recs;         // uint2 [n_recs]
+};
+
+struct BlobHeader {
+  uint32_t magic, version;
+  int32_t S, K, D, nwarps, S_pad, D_pad;
+  BlobView view[3];  // 0: by destination (alpha), 1: by source (beta), 2: by pdf (gamma)
+  int64_t off_leaky, off_init, off_final;
+  int64_t total_bytes;
+};
+
+// ------------------------------------------------------------------------------- host: packing
+namespace {
+
+struct ViewBuild {
+  std::vector<int32_t> rows, warp_ptr, warp_slices;
+  std::vector<int32_t> desc;  // 2 per slice
+  std::vector<uint32_t> rec_idx;  // a | b << 16
+  std::vector<float> rec_w;
+};
+
+// row_of[k]: key row of arc k; arcs are visited in index order (the CSR order of `trans`).
+static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, const std::vector<uint32_t> &ab,
+                       const float *w, int nwarps, ViewBuild &v) {
+  std::vector<int32_t> deg(n_rows, 0);
+  for (int k = 0; k < K; k++) deg[row_of[k]]++;
+  std::vector<int32_t> start(n_rows + 1, 0);
+  for (int r = 0; r < n_rows; r++) start[r + 1] = start[r] + deg[r];
+  std::vector<int32_t> arcs(K), fill(start.begin(), start.end() - 1);
+  for (int k = 0; k < K; k++) arcs[fill[row_of[k]]++] = k;  // stable: arc order inside a row is preserved
+  std::vector<int32_t> order(n_rows);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return deg[a] > deg[b]; });
+  const int n_slices = (n_rows + 31) / 32;
+  v.rows.assign((size_t)n_slices * 32, -1);
+  v.desc.assign((size_t)n_slices * 2, 0);
+  size_t n_recs = 0;
+  for (int s = 0; s < n_slices; s++) {
+    int width = 0;
+    for (int l = 0; l < 32; l++) {
+      const int i = s * 32 + l;
+      if (i < n_rows) { v.rows[i] = order[i]; width = std::max(width, deg[order[i]]); }
+    }
+    v.desc[2 * s] = (int32_t)n_recs;
+    v.desc[2 * s + 1] = width;
+    n_recs += (size_t)width * 32;
+  }
+  v.rec_idx.assign(n_recs, 0u);
+  v.rec_w.assign(n_recs, 0.f);
+  for (int s = 0; s < n_slices; s++) {
+    const int off = v.desc[2 * s], width = v.desc[2 * s + 1];
+    for (int l = 0; l < 32; l++) {
+      const int r = v.rows[(size_t)s * 32 + l];
+      if (r < 0) continue;
+      for (int j = 0; j < deg[r] && j < width; j++) {
+        const int k = arcs[start[r] + j];
+        v.rec_idx[(size_t)off + (size_t)j * 32 + l] = ab[k];
+        v.rec_w[(size_t)off + (size_t)j * 32 + l] = w ? w[k] : 0.f;
+      }
+    }
+  }
+  // slices -> warps: longest-processing-time first (slices are already sorted by width)
+  std::vector<long> load(nwarps, 0);
+  std::vector<std::vector<int32_t>> per(nwarps);
+  for (int s = 0; s < n_slices; s++) {
+    int best = 0;
+    for (int wv = 1; wv < nwarps; wv++)
+      if (load[wv] < load[best]) best = wv;
+    per[best].push_back(s);
+    load[best] += v.desc[2 * s + 1] + 3;
+  }
+  v.warp_ptr.assign(nwarps + 1, 0);
+  v.warp_slices.clear();
+  for (int wv = 0; wv < nwarps; wv++) {
+    v.warp_ptr[wv + 1] = v.warp_ptr[wv] + (int32_t)per[wv].size();
+    v.warp_slices.insert(v.warp_slices.end(), per[wv].begin(), per[wv].end());
+  }
+}
+
+static int64_t pack_blob(const int32_t *ft, const int32_t *fi, const float *fp, const int32_t *bt, const int32_t *bi,
+                         const float *bp, const float *leaky, const float *init, const float *fin, int S, int K, int D,
+                         void *out, int64_t out_bytes) {
+  if (S <= 0 || K <= 0 || D <= 0 || !ft || !fi || !bt || !bi) return CHAIN_B200_ERR_INVALID_ARG;
+  if (S > 65535 || D > 65535) return CHAIN_B200_ERR_UNSUPPORTED;
+  // validate the CSR: full coverage, indices in range
+  int kf = 0, kb = 0;
+  for (int s = 0; s < S; s++) {
+    if (fi[2 * s] != kf || fi[2 * s + 1] < kf || fi[2 * s + 1] > K) return CHAIN_B200_ERR_INVALID_ARG;
+    kf = fi[2 * s + 1];
+    if (bi[2 * s] != kb || bi[2 * s + 1] < kb || bi[2 * s + 1] > K) return CHAIN_B200_ERR_INVALID_ARG;
+    kb = bi[2 * s + 1];
+  }
+  if (kf != kb) return CHAIN_B200_ERR_INVALID_ARG;
+  const int Kv = kf;  // real arcs (rows beyond are padding)
+  std::vector<int32_t> row_dst(Kv), row_src(Kv), row_pdf(Kv);
+  std::vector<uint32_t> ab_fwd(Kv), ab_bwd(Kv), ab_gam(Kv);
+  for (int s = 0; s < S; s++)
+    for (int k = bi[2 * s]; k < bi[2 * s + 1]; k++)
+      if (bt[3 * k + 1] != s) return CHAIN_B200_ERR_INVALID_ARG;
+  for (int s = 0; s < S; s++)
+    for (int k = fi[2 * s]; k < fi[2 * s + 1]; k++)
+      if (ft[3 * k] != s) return CHAIN_B200_ERR_INVALID_ARG;
+  for (int k = 0; k < Kv; k++) {
+    const int32_t bs = bt[3 * k], bd = bt[3 * k + 1], bn = bt[3 * k + 2];
+    const int32_t fs = ft[3 * k], fd = ft[3 * k + 1], fn = ft[3 * k + 2];
+    if (bs < 0 || bs >= S || bd < 0 || bd >= S || bn < 0 || bn >= D) return CHAIN_B200_ERR_INVALID_ARG;
+    if (fs < 0 || fs >= S || fd < 0 || fd >= S || fn < 0 || fn >= D) return CHAIN_B200_ERR_INVALID_ARG;
+    row_dst[k] = bd; ab_fwd[k] = (uint32_t)bs | ((uint32_t)bn << 16);  // alpha pass: a = src, b = pdf (backward CSR order)
+    row_src[k] = fs; ab_bwd[k] = (uint32_t)fd | ((uint32_t)fn << 16);  // beta pass:  a = dst, b = pdf (forward CSR order)
+    row_pdf[k] = fn; ab_gam[k] = (uint32_t)fs | ((uint32_t)fd << 16);  // gamma pass: a = src, b = dst (forward CSR order)
+  }
+  ViewBuild vb[3];
+  build_view(S, Kv, row_dst, ab_fwd, bp, DEN_NW, vb[0]);
+  build_view(S, Kv, row_src, ab_bwd, fp, DEN_NW, vb[1]);
+  build_view(D, Kv, row_pdf, ab_gam, fp, DEN_NW, vb[2]);
+
+  BlobHeader h;
+  memset(&h, 0, sizeof(h));
+  h.magic = kBlobMagic; h.version = kBlobVersion;
+  h.S = S; h.K = Kv; h.D = D; h.nwarps = DEN_NW;
+  h.S_pad = (S + 3) / 4 * 4; h.D_pad = (D + 3) / 4 * 4;
+  size_t off = align_up(sizeof(BlobHeader));
+  for (int i = 0; i < 3; i++) {
+    BlobView &bv = h.view[i];
+    bv.n_rows = (i == 2) ? D : S;
+    bv.n_slices = (int32_t)(vb[i].rows.size() / 32);
+    bv.n_recs = (int64_t)vb[i].rec_idx.size();
+    bv.off_rows = (int64_t)off; off = align_up(off + vb[i].rows.size() * 4);
+    bv.off_desc = (int64_t)off; off = align_up(off + vb[i].desc.size() * 4);
+    bv.off_warp_ptr = (int64_t)off; off = align_up(off + vb[i].warp_ptr.size() * 4);
+    bv.off_warp_slices = (int64_t)off; off = align_up(off + vb[i].warp_slices.size() * 4 + 4);
+    bv.off_recs = (int64_t)off; off = align_up(off + vb[i].rec_idx.size() * 8 + 8);
+  }
+  h.off_leaky = (int64_t)off; off = align_up(off + (size_t)h.S_pad * 4);
+  h.off_init = (int64_t)off; off = align_up(off + (size_t)h.S_pad * 4);
+  h.off_final = (int64_t)off; off = align_up(off + (size_t)h.S_pad * 4);
+  h.total_bytes = (int64_t)off;
+  if (!out) return h.total_bytes;
+  if (out_bytes < h.total_bytes || !fp || !bp || !leaky || !init || !fin) return CHAIN_B200_ERR_INVALID_ARG;
+  char *base = (char *)out;
+  memset(base, 0, (size_t)h.total_bytes);
+  memcpy(base, &h, sizeof(h));
+  for (int i = 0; i < 3; i++) {
+    const BlobView &bv = h.view[i];
+    memcpy(base + bv.off_rows, vb[i].rows.data(), vb[i].rows.size() * 4);
+    memcpy(base + bv.off_desc, vb[i].desc.data(), vb[i].desc.size() * 4);
+    memcpy(base + bv.off_warp_ptr, vb[i].warp_ptr.data(), vb[i].warp_ptr.size() * 4);
+    memcpy(base + bv.off_warp_slices, vb[i].warp_slices.data(), vb[i].warp_slices.size() * 4);
+    uint32_t *rec = (uint32_t *)(base + bv.off_recs);
+    for (size_t j = 0; j < vb[i].rec_idx.size(); j++) {
+      rec[2 * j] = vb[i].rec_idx[j];
+      memcpy(&rec[2 * j + 1], &vb[i].rec_w[j], 4);
+    }
+  }
+  memcpy(base + h.off_leaky, leaky, (size_t)S * 4);
+  memcpy(base + h.off_init, init, (size_t)S * 4);
+  memcpy(base + h.off_final, fin, (size_t)S * 4);
+  return h.total_bytes;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------- device
+struct DView {
+  const int32_t *rows;
+  const int2 *desc;
+  const int32_t *warp_ptr;
+  const int32_t *warp_slices;
+  const uint2 *recs;
+};
+
+struct DenParams {
+  DView view[3];
+  const float *leaky, *init, *fin;
+  const float *x;
+  const int64_t *lengths;
+  int B, T, D, S, S_pad, D_pad;
+  float coeff;
+  unsigned flags;
+  float *logp, *grad, *diag;
+  float *alpha_ws, *tot_ws;
+  int num_groups, use_tma_x;
+};
+
+template <int G> struct Vec;
+template <> struct Vec<4> { using type = float4; };
+template <> struct Vec<2> { using type = float2; };
+template <> struct Vec<1> { using type = float; };
+
+template <int G> __device__ __forceinline__ void ld_vec(const float *p, float (&v)[G]);
+template <> __device__ __forceinline__ void ld_vec<4>(const float *p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4 *>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void ld_vec<2>(const float *p, float (&v)[2]) {
+  const float2 t = *reinterpret_cast<const float2 *>(p);
+  v[0] = t.x; v[1] = t.y;
+}
+template <> __device__ __forceinline__ void ld_vec<1>(const float *p, float (&v)[1]) { v[0] = *p; }
+
+template <int G> __device__ __forceinline__ void st_vec(float *p, const float (&v)[G]);
+template <> __device__ __forceinline__ void st_vec<4>(float *p, const float (&v)[4]) {
+  *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void st_vec<2>(float *p, const float (&v)[2]) {
+  *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+}
+template <> __device__ __forceinline__ void st_vec<1>(float *p, const float (&v)[1]) { *p = v[0]; }
+
+__device__ __forceinline__ uint2 ldg_stream(const uint2 *p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
+// ---- mbarrier / TMA bulk helpers (cp.async.bulk: SASS UBLKCP) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// One SELL pass: every lane owns one row of each of its warp's slices and
+// accumulates sum_k w_k * A[a_k][g] * Bv[b_k][g] over the row's records.
+template <int G, class Epi>
+__device__ __forceinline__ void sell_pass(const DView &v, const float *__restrict__ A, const float *__restrict__ Bv,
+                                          int warp, int lane, Epi epi) {
+  const int s1 = v.warp_ptr[warp + 1];
+  for (int si = v.warp_ptr[warp]; si < s1; si++) {
+    const int slice = v.warp_slices[si];
+    const int2 d = __ldg(&v.desc[slice]);
+    const int row = __ldg(&v.rows[slice * 32 + lane]);
+    const uint2 *rp = v.recs + d.x + lane;
+    float acc[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) acc[g] = 0.f;
+    int k = 0;
+    for (; k + 4 <= d.y; k += 4) {
+      uint2 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) r[u] = ldg_stream(rp + (k + u) * 32);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        float a[G], b[G];
+        ld_vec<G>(A + (r[u].x & 0xffffu) * G, a);
+        ld_vec<G>(Bv + (r[u].x >> 16) * G, b);
+        const float w = __uint_as_float(r[u].y);
+#pragma unroll
+        for (int g = 0; g < G; g++) acc[g] = fmaf(a[g] * w, b[g], acc[g]);
+      }
+    }
+    for (; k < d.y; k++) {
+      const uint2 r = ldg_stream(rp + k * 32);
+      float a[G], b[G];
+      ld_vec<G>(A + (r.x & 0xffffu) * G, a);
+      ld_vec<G>(Bv + (r.x >> 16) * G, b);
+      const float w = __uint_as_float(r.y);
+#pragma unroll
+      for (int g = 0; g < G; g++) acc[g] = fmaf(a[g] * w, b[g], acc[g]);
+    }
+    epi(row, acc);
+  }
+}
+
+// sum over the block of G per-thread values; result to every thread.
+template <int G>
+__device__ __forceinline__ void block_sum_vec(float (&v)[G], float *red /* [DEN_NW*G] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+    v[g] = warp_sum(v[g]);
+    if (lane == 0) red[warp * G + g] = v[g];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+    float t = 0.f;
+    for (int w = 0; w < DEN_NW; w++) t += red[w * G + g];
+    v[g] = t;
+  }
+  __syncthreads();
+}
+
+template <int G>
+__global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long mbar[2];  // 0: alpha rows, 1: x frames
+  __shared__ float red[DEN_NW * 4];
+  __shared__ float red2[DEN_NW * 4];
+
+  const int S = p.S, D = p.D, T = p.T, S_pad = p.S_pad, D_pad = p.D_pad;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float c = p.coeff;
+  float *buf0 = reinterpret_cast<float *>(smem_raw);
+  float *buf1 = buf0 + (size_t)S_pad * G;
+  float *x_s = buf1 + (size_t)S_pad * G;
+  float *xraw = x_s + (size_t)D_pad * G;
+  float *gam_s = xraw + (size_t)D_pad * G;
+  const float *__restrict__ lk = p.leaky;
+  const float *__restrict__ ini = p.init;
+  const float *__restrict__ fin = p.fin;
+  const bool clamp_x = (p.flags & CHAIN_B200_CLAMP_X) && !(p.flags & CHAIN_B200_X_IS_EXP);
+  const bool exp_x = !(p.flags & CHAIN_B200_X_IS_EXP);
+
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t ph_a = 0, ph_x = 0;
+
+  // graph constants: sum_i init_i and sum_i final_i * leaky_i
+  float tot0, FL;
+  {
+    float v[2] = {0.f, 0.f};
+    for (int i = tid; i < S; i += DEN_NT) { v[0] += ini[i]; v[1] += fin[i] * lk[i]; }
+    block_sum_vec<2>(v, red);
+    tot0 = v[0]; FL = v[1];
+  }
+
+  for (int gi = blockIdx.x; gi < p.num_groups; gi += gridDim.x) {
+    const int b0 = gi * G;
+    int Lg[G];
+    int Lmax = 0;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      long long l = (b0 + g < p.B) ? p.lengths[b0 + g] : 0;
+      Lg[g] = (int)(l < 0 ? 0 : (l > T ? T : l));
+      Lmax = max(Lmax, Lg[g]);
+    }
+    float *aws = p.alpha_ws + (size_t)gi * (T + 1) * S_pad * G;
+    float *tws = p.tot_ws + (size_t)gi * (T + 1) * G;
+    const float *xg[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) xg[g] = p.x + (size_t)min(b0 + g, p.B - 1) * T * D;
+
+    // stage one frame of x: TMA bulk copies into xraw (one per live utterance) ...
+    auto issue_x = [&](int f) {
+      if (!p.use_tma_x) return;
+      if (tid == 0) {
+        fence_proxy_async();
+        uint32_t bytes = 0;
+#pragma unroll
+        for (int g = 0; g < G; g++) bytes += (f < Lg[g]) ? (uint32_t)D * 4u : 0u;
+        mbar_expect_tx(&mbar[1], bytes);
+#pragma unroll
+        for (int g = 0; g < G; g++)
+          if (f < Lg[g]) tma_load_1d(xraw + (size_t)g * D_pad, xg[g] + (size_t)f * D, (uint32_t)D * 4u, &mbar[1]);
+      }
+    };
+    // ... then clamp / exp while transposing into the interleaved x_s[pdf][g]; dead lanes get 0
+    auto transform_x = [&](int f) {
+      if (p.use_tma_x) { mbar_wait(&mbar[1], ph_x); ph_x ^= 1u; }
+      for (int n = tid; n < D; n += DEN_NT) {
+        float v[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+          float t = 0.f;
+          if (f < Lg[g]) {
+            t = p.use_tma_x ? xraw[(size_t)g * D_pad + n] : __ldg(xg[g] + (size_t)f * D + n);
+            if (clamp_x) t = clampf(t, kClampLo, kClampHi);
+            if (exp_x) t = __expf(t);
+          }
+          v[g] = t;
+        }
+        st_vec<G>(x_s + (size_t)n * G, v);
+      }
+    };
+
+    double logp[G];
+    float invZ[G], tot[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) { logp[g] = 0.0; invZ[g] = 0.f; }
+
+    // ============================================================ forward
+    float *A = buf0, *Bn = buf1;  // A: alpha'(t-1) (read), Bn: alpha(t) (written)
+    __syncthreads();               // previous group is completely done with smem
+    if (Lmax > 0) issue_x(0);
+    // t = 0 : alpha(0) = init (same for every utterance), alpha' = alpha + c*tot*leaky
+    {
+      bool need_z = false;
+#pragma unroll
+      for (int g = 0; g < G; g++) { tot[g] = tot0; need_z |= (Lg[g] == 0); }
+      float zp[G];
+#pragma unroll
+      for (int g = 0; g < G; g++) zp[g] = 0.f;
+      const float ct = c * tot0;
+      for (int i = tid; i < S_pad; i += DEN_NT) {
+        float v[G];
+        const float a = (i < S) ? ini[i] + ct * lk[i] : 0.f;
+        const float f = (need_z && i < S) ? fin[i] : 0.f;
+#pragma unroll
+        for (int g = 0; g < G; g++) { v[g] = a; zp[g] += a * f; }
+        st_vec<G>(A + (size_t)i * G, v);
+        st_vec<G>(aws + (size_t)i * G, v);
+      }
+      if (tid == 0) {
+        float tv[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) { tv[g] = tot0; if (0 < Lg[g]) logp[g] += (double)logf(tot0); }
+        st_vec<G>(tws, tv);
+      }
+      if (need_z) {
+        block_sum_vec<G>(zp, red2);
+#pragma unroll
+        for (int g = 0; g < G; g++)
+          if (Lg[g] == 0) { invZ[g] = 1.0f / zp[g]; logp[g] += (double)logf(zp[g]); }
+      }
+    }
+    __syncthreads();
+
+    for (int t = 1; t <= Lmax; t++) {
+      transform_x(t - 1);
+      __syncthreads();  // x_s complete, xraw free
+      if (t < Lmax) issue_x(t);
+      float inv[G], part[G];
+#pragma unroll
+      for (int g = 0; g < G; g++) { inv[g] = tot[g] > 0.f ? 1.0f / tot[g] : 0.f; part[g] = 0.f; }
+      sell_pass<G>(p.view[0], A, x_s, warp, lane, [&](int row, const float (&acc)[G]) {
+        if (row >= 0) {
+          float o[G];
+#pragma unroll
+          for (int g = 0; g < G; g++) { o[g] = acc[g] * inv[g]; part[g] += o[g]; }
+          st_vec<G>(Bn + (size_t)row * G, o);
+        }
+      });
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        part[g] = warp_sum(part[g]);
+        if (lane == 0) red[warp * G + g] = part[g];
+      }
+      __syncthreads();  // alpha(t) rows + partial sums visible; everybody done reading A
+      bool need_z = false;
+      float ct[G], zp[G];
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        float s = 0.f;
+        for (int w = 0; w < DEN_NW; w++) s += red[w * G + g];
+        tot[g] = s; ct[g] = c * s; zp[g] = 0.f;
+        need_z |= (Lg[g] == t);
+      }
+      float *awt = aws + (size_t)t * S_pad * G;
+      for (int i = tid; i < S; i += DEN_NT) {
+        float v[G];
+        ld_vec<G>(Bn + (size_t)i * G, v);
+        const float l = __ldg(lk + i);
+        const float f = need_z ? __ldg(fin + i) : 0.f;
+#pragma unroll
+        for (int g = 0; g < G; g++) { v[g] = fmaf(ct[g], l, v[g]); zp[g] += v[g] * f; }
+        st_vec<G>(Bn + (size_t)i * G, v);
+        st_vec<G>(awt + (size_t)i * G, v);
+      }
+      if (tid == 0) {
+        float tv[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) { tv[g] = tot[g]; if (t < Lg[g]) logp[g] += (double)logf(tot[g]); }
+        st_vec<G>(tws + (size_t)t * G, tv);
+      }
+      if (need_z) {
+        block_sum_vec<G>(zp, red2);
+#pragma unroll
+        for (int g = 0; g < G; g++)
+          if (Lg[g] == t) { invZ[g] = 1.0f / zp[g]; logp[g] += (double)logf(zp[g]); }
+      }
+      float *tmp = A; A = Bn; Bn = tmp;
+      __syncthreads();
+    }
+    if (tid == 0) {
+#pragma unroll
+      for (int g = 0; g < G; g++)
+        if (b0 + g < p.B) p.logp[b0 + g] = (float)logp[g];
+    }
+
+    // ============================================================ backward
+    // P: alpha'(t) (TMA-loaded), Q: beta(t+1).  Both forward buffers are free now.
+    float *P = buf0, *Q = buf1;
+    for (int i = tid; i < S_pad * G; i += DEN_NT) Q[i] = 0.f;
+    if (Lmax > 0) issue_x(Lmax - 1);
+    __syncthreads();
+    for (int t = Lmax - 1; t >= 0; t--) {
+      // utterances that end at t+1 enter here: beta(L) = final/Z + c * sum_k final_k leaky_k / Z
+      bool inject = false;
+#pragma unroll
+      for (int g = 0; g < G; g++) inject |= (Lg[g] == t + 1);
+      if (tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&mbar[0], (uint32_t)S_pad * G * 4u);
+        tma_load_1d(P, aws + (size_t)t * S_pad * G, (uint32_t)S_pad * G * 4u, &mbar[0]);
+      }
+      if (inject) {
+        for (int i = tid; i < S; i += DEN_NT) {
+          float v[G];
+          ld_vec<G>(Q + (size_t)i * G, v);
+          const float f = __ldg(fin + i);
+#pragma unroll
+          for (int g = 0; g < G; g++)
+            if (Lg[g] == t + 1) v[g] = fmaf(c * invZ[g], FL, invZ[g] * f);
+          st_vec<G>(Q + (size_t)i * G, v);
+        }
+      }
+      transform_x(t);
+      float inv[G];
+      {
+        float tv[G];
+        ld_vec<G>(tws + (size_t)t * G, tv);
+#pragma unroll
+        for (int g = 0; g < G; g++) inv[g] = (t < Lg[g] && tv[g] > 0.f) ? 1.0f / tv[g] : 0.f;
+      }
+      mbar_wait(&mbar[0], ph_a); ph_a ^= 1u;
+      __syncthreads();  // P, Q, x_s ready; xraw free
+      if (t > 0) issue_x(t - 1);
+
+      // ---- gamma pass: rows = pdfs; gamma(t,n) = x(t,n)/tot(t) * sum alpha'(src) p beta(dst)
+      float gsum[G];
+#pragma unroll
+      for (int g = 0; g < G; g++) gsum[g] = 0.f;
+      sell_pass<G>(p.view[2], P, Q, warp, lane, [&](int row, const float (&acc)[G]) {
+        if (row >= 0) {
+          float xv[G], o[G];
+          ld_vec<G>(x_s + (size_t)row * G, xv);
+#pragma unroll
+          for (int g = 0; g < G; g++) { o[g] = acc[g] * xv[g] * inv[g]; gsum[g] += o[g]; }
+          st_vec<G>(gam_s + (size_t)row * G, o);
+        }
+      });
+      __syncthreads();  // gamma rows complete; everybody done reading P
+
+      // ---- beta' pass: rows = source states; beta'(t,i) = sum p beta(t+1,dst) x(t,pdf) / tot(t)
+      float lpart[G], ab[G];
+#pragma unroll
+      for (int g = 0; g < G; g++) { lpart[g] = 0.f; ab[g] = 0.f; }
+      sell_pass<G>(p.view[1], Q, x_s, warp, lane, [&](int row, const float (&acc)[G]) {
+        if (row >= 0) {
+          float o[G];
+          const float l = __ldg(lk + row);
+          if (t == 0) {
+            float av[G];
+            ld_vec<G>(P + (size_t)row * G, av);
+#pragma unroll
+            for (int g = 0; g < G; g++) ab[g] = fmaf(av[g], acc[g] * inv[g], ab[g]);
+          }
+#pragma unroll
+          for (int g = 0; g < G; g++) { o[g] = acc[g] * inv[g]; lpart[g] = fmaf(o[g], l, lpart[g]); }
+          st_vec<G>(P + (size_t)row * G, o);
+        }
+      });
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        lpart[g] = warp_sum(lpart[g]);
+        if (lane == 0) red[warp * G + g] = lpart[g];
+      }
+      // write this frame's gradient rows (coalesced over pdfs) while the other warps finish
+      for (int g = 0; g < G; g++) {
+        if (b0 + g >= p.B) break;
+        float *gr = p.grad + ((size_t)(b0 + g) * T + t) * D;
+        const bool live = t < Lg[g];
+        for (int n = tid; n < D; n += DEN_NT) gr[n] = live ? gam_s[(size_t)n * G + g] : 0.f;
+      }
+      __syncthreads();  // beta' rows + partials visible; everybody done reading Q and gam_s
+      float cb[G];
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        float s = 0.f;
+        for (int w = 0; w < DEN_NW; w++) s += red[w * G + g];
+        cb[g] = c * s;
+      }
+      for (int i = tid; i < S; i += DEN_NT) {
+        float v[G];
+        ld_vec<G>(P + (size_t)i * G, v);
+#pragma unroll
+        for (int g = 0; g < G; g++) v[g] += cb[g];
+        st_vec<G>(P + (size_t)i * G, v);
+      }
+      if (t == 0) {  // the reference's self-check quantities (chain-computation.cc:363-371)
+        block_sum_vec<G>(ab, red2);
+        block_sum_vec<G>(gsum, red2);
+        if (tid == 0) {
+#pragma unroll
+          for (int g = 0; g < G; g++)
+            if (b0 + g < p.B) { p.diag[2 * (b0 + g)] = ab[g]; p.diag[2 * (b0 + g) + 1] = gsum[g]; }
+        }
+      }
+      float *tmp = P; P = Q; Q = tmp;  // Q <- beta(t); P <- free
+      __syncthreads();
+    }
+    // utterances of length 0 and padded frames t >= Lmax
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      if (b0 + g >= p.B) continue;
+      if (Lg[g] == 0 && tid == 0) { p.diag[2 * (b0 + g)] = 1.f; p.diag[2 * (b0 + g) + 1] = 1.f; }
+      float *gr = p.grad + ((size_t)(b0 + g) * T + Lmax) * D;
+      const size_t n = (size_t)(T - Lmax) * D;
+      for (size_t i = tid; i < n; i += DEN_NT) gr[i] = 0.f;
+    }
+  }
+}
+
+// objf / ok reduction (defined in generic.cu)
+__global__ void finalize_kernel(const float *logp, const float *diag, int B, int check_ab, float *objf, int32_t *ok,
+                                float *diag_out);
+
+struct DenWs {
+  size_t alpha, tot, logp, diag, total;
+};
+static DenWs den_ws_layout(const BlobHeader &h, int B, int T) {
+  DenWs w;
+  size_t off = 0;
+  const size_t Bp = (size_t)B + 3;
+  w.alpha = off; off = align_up(off + sizeof(float) * Bp * (T + 1) * h.S_pad);
+  w.tot = off; off = align_up(off + sizeof(float) * Bp * (T + 1));
+  w.logp = off; off = align_up(off + sizeof(float) * Bp);
+  w.diag = off; off = align_up(off + sizeof(float) * 2 * Bp);
+  w.total = off;
+  return w;
+}
+
+static size_t den_smem_bytes(const BlobHeader &h, int G) {
+  return sizeof(float) * ((size_t)2 * h.S_pad * G + (size_t)3 * h.D_pad * G) + 128;
+}
+
+// Relative cost of one frame for a group of G utterances (shared-memory wavefronts of
+// the vector gathers), used to pick G: time ~ waves(G) * cost(G).
+static int choose_G(const BlobHeader &h, int B, int num_sms) {
+  const char *env = getenv("CHAIN_B200_G");
+  if (env) {
+    const int g = atoi(env);
+    if ((g == 1 || g == 2 || g == 4) && den_smem_bytes(h, g) <= 227 * 1024) return g;
+  }
+  const double cost[5] = {0, 0.36, 0.62, 0, 1.0};
+  int best = 0;
+  double best_t = 1e30;
+  for (int g : {4, 2, 1}) {
+    if (den_smem_bytes(h, g) > 227 * 1024) continue;
+    const int groups = (B + g - 1) / g;
+    const double t = (double)((groups + num_sms - 1) / num_sms) * cost[g];
+    if (t < best_t - 1e-9) { best_t = t; best = g; }
+  }
+  return best;
+}
+
+}  // namespace chainb200
+
+using namespace chainb200;
+
+extern "C" {
+
+int64_t chain_b200_den_prepare_bytes(const int32_t *ft, const int32_t *fi, const int32_t *bt, const int32_t *bi, int S,
+                                     int K, int D) {
+  return pack_blob(ft, fi, nullptr, bt, bi, nullptr, nullptr, nullptr, nullptr, S, K, D, nullptr, 0);
+}
+
+int chain_b200_den_prepare(const int32_t *ft, const int32_t *fi, const float *fp, const int32_t *bt,
+                           const int32_t *bi, const float *bp, const float *leaky, const float *init,
+                           const float *fin, int S, int K, int D, void *blob, int64_t blob_bytes) {
+  if (!blob) return CHAIN_B200_ERR_INVALID_ARG;
+  const int64_t r = pack_blob(ft, fi, fp, bt, bi, bp, leaky, init, fin, S, K, D, blob, blob_bytes);
+  return r < 0 ? (int)r : CHAIN_B200_OK;
+}
+
+size_t chain_b200_den_workspace_bytes(const void *blob_host, int B, int T) {
+  const BlobHeader *h = (const BlobHeader *)blob_host;
+  if (!h || h->magic != kBlobMagic || h->version != kBlobVersion || B <= 0 || T <= 0) return 0;
+  return den_ws_layout(*h, B, T).total;
+}
+
+int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev, const float *x,
+                                    const int64_t *lengths, int B, int T, int D, float coeff, unsigned flags,
+                                    float *objf, float *logp, float *grad, int32_t *ok, float *diag, void *ws,
+                                    size_t ws_bytes, int device, void *stream_v) {
+  g_launch_count = 0;
+  const BlobHeader *hp = (const BlobHeader *)blob_host;
+  if (!hp || !blob_dev) return CHAIN_B200_ERR_INVALID_ARG;
+  if (hp->magic != kBlobMagic || hp->version != kBlobVersion || hp->nwarps != DEN_NW) return CHAIN_B200_ERR_BAD_BLOB;
+  const BlobHeader h = *hp;
+  if (B <= 0 || T <= 0 || D != h.D || !x || !lengths || !objf || !grad || !ok) return CHAIN_B200_ERR_INVALID_ARG;
+  if (!(coeff > 0.f && coeff < 1.f)) return CHAIN_B200_ERR_INVALID_ARG;  // chain-computation.cc:68
+  const DenWs w = den_ws_layout(h, B, T);
+  if (!ws || ws_bytes < w.total) return CHAIN_B200_ERR_WORKSPACE;
+
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return (int)guard.err;
+  int num_sms = 148;
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device);
+  const int G = choose_G(h, B, num_sms);
+  if (G == 0) return CHAIN_B200_ERR_UNSUPPORTED;
+  const size_t smem = den_smem_bytes(h, G);
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  const char *bd = (const char *)blob_dev;
+  char *base = (char *)ws;
+
+  DenParams p;
+  for (int i = 0; i < 3; i++) {
+    p.view[i].rows = (const int32_t *)(bd + h.view[i].off_rows);
+    p.view[i].desc = (const int2 *)(bd + h.view[i].off_desc);
+    p.view[i].warp_ptr = (const int32_t *)(bd + h.view[i].off_warp_ptr);
+    p.view[i].warp_slices = (const int32_t *)(bd + h.view[i].off_warp_slices);
+    p.view[i].recs = (const uint2 *)(bd + h.view[i].off_recs);
+  }
+  p.leaky = (const float *)(bd + h.off_leaky);
+  p.init = (const float *)(bd + h.off_init);
+  p.fin = (const float *)(bd + h.off_final);
+  p.x = x; p.lengths = lengths;
+  p.B = B; p.T = T; p.D = D; p.S = h.S; p.S_pad = h.S_pad; p.D_pad = h.D_pad;
+  p.coeff = coeff; p.flags = flags;
+  p.logp = logp ? logp : (float *)(base + w.logp);
+  p.grad = grad;
+  p.diag = (float *)(base + w.diag);
+  p.alpha_ws = (float *)(base + w.alpha);
+  p.tot_ws = (float *)(base + w.tot);
+  p.num_groups = (B + G - 1) / G;
+  p.use_tma_x = (D % 4 == 0) && (((uintptr_t)x & 15u) == 0);
+
+  const int grid = std::min(p.num_groups, num_sms);
+  cudaError_t e;
+#define LAUNCH_DEN(GG)                                                                                          \
+  do {                                                                                                          \
+    e = cudaFuncSetAttribute(den_shared_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e != cudaSuccess) return (int)e;                                                                        \
+    den_shared_kernel<GG><<<grid, DEN_NT, smem, stream>>>(p);                                                   \
+  } while (0)
+  if (G == 4) LAUNCH_DEN(4);
+  else if (G == 2) LAUNCH_DEN(2);
+  else LAUNCH_DEN(1);
+#undef LAUNCH_DEN
+  g_launch_count++;
+  finalize_kernel<<<1, 256, 0, stream>>>(p.logp, p.diag, B, 1, objf, ok, diag);
+  g_launch_count++;
+  e = cudaGetLastError();
+  return (int)e;
+}
+
+}  // extern "C"

@@ -1,0 +1,502 @@
+// generic.cu -- per-sequence-graph forward-backward (both semirings), sm_100a.
+//
+// One persistent CTA per utterance walks the whole alpha/beta recursion: no
+// per-frame host loop, no per-frame launches (the reference issues ~8 launches
+// per frame).  Replaces, for arbitrary per-sequence graphs in the
+// reference's [B,K,3] layout:
+//   ChainComputation            /root/reference/pytorch_binding/src/chain-computation.cc:24-391
+//   ChainLogDomainComputation   /root/reference/pytorch_binding/src/chain-log-domain-computation.cc:25-304
+//   the 4 kernels               chain-kernels.cu:97-245, chain-log-domain-kernels.cu:86-235
+//
+// Data layout per CTA (shared memory): three state rows (alpha(t-1)/alpha(t) in
+// the forward pass; alpha'(t), beta(t+1), beta(t) in the backward pass) + the
+// current frame of (exp) log-probs.  alpha' rows are spilled to the HBM
+// workspace [B,T+1,S] for the backward pass.  The arc-posterior gradient is
+// accumulated WITHOUT atomics: a third, pdf-sorted view of the arcs is built
+// once per call (pdf_sort_kernel) and gamma(t,n) is a segmented sum owned by the
+// thread of pdf n, written coalesced and exactly once (the reference uses
+// thresholded atomicAdd / atomicCAS log-add per arc, chain-kernels.cu:53-87,
+// chain-log-domain-kernels.cu:62-75).
+#include "common.cuh"
+
+namespace chainb200 {
+
+thread_local int g_launch_count = 0;
+int g_verbose_level = 0;
+
+constexpr int GEN_NT = 256;
+
+struct GenericParams {
+  const int32_t *ft, *fi, *bt, *bi;
+  const float *fp, *bp, *leaky, *init, *fin;
+  const float *x;
+  const int64_t *lengths;
+  int B, T, D, S, K;
+  float coeff;
+  unsigned flags;
+  float *logp, *grad, *diag;  // diag: [B][2]
+  float *alpha_ws, *tot_ws;   // [B][T+1][S], [B][T+1]
+  const int32_t *pdf_ptr;     // [Bg][D+1]
+  const uint2 *pdf_rec;       // [Bg][K]  {src | dst<<16, weight bits}
+};
+
+// ---------------------------------------------------------------- pdf-sorted view
+// Stable counting sort of one graph's arcs by pdf id.  grid = Bg, block = 128.
+// smem: (D+1) ints.
+__global__ void __launch_bounds__(128) pdf_sort_kernel(const int32_t *__restrict__ ft_all,
+                                                       const int32_t *__restrict__ fi_all,
+                                                       const float *__restrict__ fp_all, int S, int K, int D,
+                                                       int32_t *__restrict__ pdf_ptr_all,
+                                                       uint2 *__restrict__ pdf_rec_all) {
+  extern __shared__ int cnt[];  // D + 1
+  __shared__ int red[4];
+  const int g = blockIdx.x;
+  const int32_t *ft = ft_all + (size_t)g * K * 3;
+  const int32_t *fi = fi_all + (size_t)g * S * 2;
+  const float *fp = fp_all + (size_t)g * K;
+  int32_t *pdf_ptr = pdf_ptr_all + (size_t)g * (D + 1);
+  uint2 *rec = pdf_rec_all + (size_t)g * K;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // number of real arcs = largest row end (padded arcs of initialized_by_list lie beyond it)
+  int kv = 0;
+  for (int s = tid; s < S; s += blockDim.x) kv = max(kv, fi[2 * s + 1]);
+  for (int o = 16; o > 0; o >>= 1) kv = max(kv, __shfl_xor_sync(0xffffffffu, kv, o));
+  if (lane == 0) red[warp] = kv;
+  for (int n = tid; n <= D; n += blockDim.x) cnt[n] = 0;
+  __syncthreads();
+  kv = min(K, max(max(red[0], red[1]), max(red[2], red[3])));
+  for (int k = tid; k < kv; k += blockDim.x) {
+    const int pdf = ft[3 * k + 2];
+    if (pdf >= 0 && pdf < D) atomicAdd(&cnt[pdf], 1);
+  }
+  __syncthreads();
+  // exclusive scan of cnt[0..D) by warp 0 (chunks of 32 with a running carry)
+  if (warp == 0) {
+    int carry = 0;
+    for (int base = 0; base < D; base += 32) {
+      const int n = base + lane;
+      const int c = (n < D) ? cnt[n] : 0;
+      int incl = c;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (n < D) { cnt[n] = carry + incl - c; pdf_ptr[n] = carry + incl - c; }
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) { cnt[D] = carry; pdf_ptr[D] = carry; }
+    __syncwarp();
+    // stable placement: arcs in index order, 32 at a time; equal pdfs inside a
+    // chunk keep their order through the match mask.
+    for (int base = 0; base < kv; base += 32) {
+      const int k = base + lane;
+      int pdf = -1;
+      if (k < kv) { pdf = ft[3 * k + 2]; if (pdf < 0 || pdf >= D) pdf = -1; }
+      const unsigned peers = __match_any_sync(0xffffffffu, pdf);
+      if (pdf >= 0) {
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int pos = cnt[pdf] + rank;
+        const unsigned src = (unsigned)ft[3 * k], dst = (unsigned)ft[3 * k + 1];
+        rec[pos] = make_uint2((src & 0xffffu) | (dst << 16), __float_as_uint(fp[k]));
+      }
+      __syncwarp();
+      if (pdf >= 0 && (peers & ((1u << lane) - 1u)) == 0) cnt[pdf] += __popc(peers);
+      __syncwarp();
+    }
+  }
+}
+
+// ---------------------------------------------------------------- main kernel
+__device__ __forceinline__ float load_x(const float *__restrict__ p, unsigned flags, bool log_domain) {
+  float v = __ldg(p);
+  const bool is_exp = !log_domain && (flags & CHAIN_B200_X_IS_EXP);
+  if ((flags & CHAIN_B200_CLAMP_X) && !is_exp) v = clampf(v, kClampLo, kClampHi);
+  if (!log_domain && !is_exp) v = expf(v);
+  return v;
+}
+
+template <bool LOG>
+__global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericParams p) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float scratch[64];
+  const int S = p.S, D = p.D, T = p.T, K = p.K;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const size_t gb = (p.flags & CHAIN_B200_GRAPH_SHARED) ? 0 : (size_t)b;
+  const int32_t *__restrict__ ft = p.ft + gb * K * 3;
+  const int32_t *__restrict__ fi = p.fi + gb * S * 2;
+  const int32_t *__restrict__ bt = p.bt + gb * K * 3;
+  const int32_t *__restrict__ bi = p.bi + gb * S * 2;
+  const float *__restrict__ fp = p.fp + gb * K;
+  const float *__restrict__ bp = p.bp + gb * K;
+  const float *__restrict__ lk = LOG ? nullptr : p.leaky + gb * S;
+  const float *__restrict__ ini = p.init + gb * S;
+  const float *__restrict__ fin = p.fin + gb * S;
+  const int32_t *__restrict__ pptr = p.pdf_ptr + gb * (D + 1);
+  const uint2 *__restrict__ prec = p.pdf_rec + gb * K;
+  const float *__restrict__ x = p.x + (size_t)b * T * D;
+  float *__restrict__ grad = p.grad + (size_t)b * T * D;
+  float *__restrict__ alpha_ws = p.alpha_ws + (size_t)b * (T + 1) * S;
+  float *__restrict__ tot_ws = p.tot_ws + (size_t)b * (T + 1);
+  long long Lraw = p.lengths[b];
+  const int L = (int)(Lraw < 0 ? 0 : (Lraw > T ? T : Lraw));
+  const float c = p.coeff;
+
+  float *bufA = smem, *bufB = smem + S, *bufC = smem + 2 * S, *x_s = smem + 3 * S;
+  double logp = 0.0;  // only thread 0's copy is used
+
+  // ------------------------------------------------------------ forward, t = 0
+  float tot_prev;
+  if (!LOG) {
+    float local = 0.f;
+    for (int i = tid; i < S; i += GEN_NT) { const float a = ini[i]; bufA[i] = a; local += a; }
+    const float tot = block_sum(local, scratch);
+    const float ct = c * tot;
+    for (int i = tid; i < S; i += GEN_NT) {
+      const float a = bufA[i] + ct * lk[i];
+      bufA[i] = a;
+      alpha_ws[i] = a;
+    }
+    if (tid == 0) { tot_ws[0] = tot; if (0 < L) logp += (double)logf(tot); }
+    tot_prev = tot;
+  } else {
+    for (int i = tid; i < S; i += GEN_NT) { const float a = ini[i]; bufA[i] = a; alpha_ws[i] = a; }
+    if (tid == 0) tot_ws[0] = 0.f;
+    tot_prev = 0.f;  // the reference stores 0 as the frame-0 alpha-sum (chain-log-domain-computation.cc:89)
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------ forward, t = 1..L
+  for (int t = 1; t <= L; t++) {
+    const float *xr = x + (size_t)(t - 1) * D;
+    for (int n = tid; n < D; n += GEN_NT) x_s[n] = load_x(xr + n, p.flags, LOG);
+    __syncthreads();
+    float tot;
+    if (!LOG) {
+      const float inv = 1.0f / tot_prev;
+      float local = 0.f;
+      for (int h = tid; h < S; h += GEN_NT) {
+        float acc = 0.f;
+        const int k1 = bi[2 * h + 1];
+        for (int k = bi[2 * h]; k < k1; k++) {
+          const int src = bt[3 * k], pdf = bt[3 * k + 2];
+          acc += bufA[src] * bp[k] * x_s[pdf];
+        }
+        const float a = acc * inv;
+        bufB[h] = a;
+        local += a;
+      }
+      tot = block_sum(local, scratch);
+      const float ct = c * tot;
+      float *aw = alpha_ws + (size_t)t * S;
+      for (int h = tid; h < S; h += GEN_NT) {
+        const float a = bufB[h] + ct * lk[h];
+        bufB[h] = a;
+        aw[h] = a;
+      }
+      if (tid == 0) { tot_ws[t] = tot; if (t < L) logp += (double)logf(tot); }
+    } else {
+      float m_loc = -INFINITY, s_loc = 0.f;
+      float *aw = alpha_ws + (size_t)t * S;
+      for (int h = tid; h < S; h += GEN_NT) {
+        const int k0 = bi[2 * h], k1 = bi[2 * h + 1];
+        float m = -INFINITY;
+        for (int k = k0; k < k1; k++) m = fmaxf(m, bufA[bt[3 * k]] + bp[k] + x_s[bt[3 * k + 2]]);
+        float a = -INFINITY;
+        if (m > -INFINITY) {
+          float s = 0.f;
+          for (int k = k0; k < k1; k++) s += expf(bufA[bt[3 * k]] + bp[k] + x_s[bt[3 * k + 2]] - m);
+          a = m + logf(s) - tot_prev;
+        }
+        bufB[h] = a;
+        aw[h] = a;
+        lse_merge(m_loc, s_loc, a, (a > -INFINITY) ? 1.f : 0.f);
+      }
+      tot = block_lse(m_loc, s_loc, scratch);
+      if (tid == 0) { tot_ws[t] = tot; if (t < L && tot > -INFINITY) logp += (double)tot; }
+    }
+    tot_prev = tot;
+    float *tmp = bufA; bufA = bufB; bufB = tmp;
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------ total likelihood, beta(L)
+  float inv_Z = 0.f, lZ = 0.f;
+  if (!LOG) {
+    float local = 0.f;
+    for (int i = tid; i < S; i += GEN_NT) local += bufA[i] * fin[i];
+    const float Z = block_sum(local, scratch);
+    if (tid == 0) logp += (double)logf(Z);
+    inv_Z = 1.0f / Z;
+    local = 0.f;
+    for (int i = tid; i < S; i += GEN_NT) local += (inv_Z * fin[i]) * lk[i];
+    const float bs = block_sum(local, scratch);
+    for (int i = tid; i < S; i += GEN_NT) bufB[i] = inv_Z * fin[i] + c * bs;
+  } else {
+    float m_loc = -INFINITY, s_loc = 0.f;
+    for (int i = tid; i < S; i += GEN_NT) {
+      const float v = bufA[i] + fin[i];
+      lse_merge(m_loc, s_loc, v, (v > -INFINITY) ? 1.f : 0.f);
+    }
+    lZ = block_lse(m_loc, s_loc, scratch);
+    if (tid == 0) logp += (double)lZ;
+    for (int i = tid; i < S; i += GEN_NT) bufB[i] = fin[i] - lZ;
+  }
+  if (tid == 0 && p.logp) p.logp[b] = (float)logp;
+  __syncthreads();
+
+  // ------------------------------------------------------------ backward, t = L-1..0
+  for (int t = L - 1; t >= 0; t--) {
+    const float *xr = x + (size_t)t * D;
+    const float *aw = alpha_ws + (size_t)t * S;
+    for (int n = tid; n < D; n += GEN_NT) x_s[n] = load_x(xr + n, p.flags, LOG);
+    for (int i = tid; i < S; i += GEN_NT) bufA[i] = aw[i];
+    const float tot_t = tot_ws[t];
+    __syncthreads();
+    float *gr = grad + (size_t)t * D;
+    float gsum = 0.f;
+    if (!LOG) {
+      const float inv = 1.0f / tot_t;
+      // gamma pass: pdf-sorted arcs, thread owns pdf n
+      for (int n = tid; n < D; n += GEN_NT) {
+        float g = 0.f;
+        const int j1 = pptr[n + 1];
+        for (int j = pptr[n]; j < j1; j++) {
+          const uint2 r = prec[j];
+          g += bufA[r.x & 0xffffu] * __uint_as_float(r.y) * bufB[r.x >> 16];
+        }
+        const float gam = g * x_s[n] * inv;
+        gr[n] = gam;
+        gsum += gam;
+      }
+      // beta' pass: thread owns source state h
+      float local = 0.f;
+      for (int h = tid; h < S; h += GEN_NT) {
+        float acc = 0.f;
+        const int k1 = fi[2 * h + 1];
+        for (int k = fi[2 * h]; k < k1; k++) acc += fp[k] * bufB[ft[3 * k + 1]] * x_s[ft[3 * k + 2]];
+        const float bd = acc * inv;
+        bufC[h] = bd;
+        local += bd * lk[h];
+      }
+      const float bs = block_sum(local, scratch);
+      if (t == 0 && p.diag) {
+        float ab = 0.f;
+        for (int i = tid; i < S; i += GEN_NT) ab += bufA[i] * bufC[i];
+        ab = block_sum(ab, scratch);
+        gsum = block_sum(gsum, scratch);
+        if (tid == 0) { p.diag[2 * b] = ab; p.diag[2 * b + 1] = gsum; }
+      }
+      const float cb = c * bs;
+      for (int h = tid; h < S; h += GEN_NT) bufC[h] += cb;
+    } else {
+      for (int n = tid; n < D; n += GEN_NT) {
+        const int j0 = pptr[n], j1 = pptr[n + 1];
+        const float xn = x_s[n] - tot_t;
+        float m = -INFINITY;
+        for (int j = j0; j < j1; j++) {
+          const uint2 r = prec[j];
+          m = fmaxf(m, bufA[r.x & 0xffffu] + __uint_as_float(r.y) + bufB[r.x >> 16] + xn);
+        }
+        float lg = -INFINITY, gam = 0.f;
+        if (m > -INFINITY) {
+          float s = 0.f;
+          for (int j = j0; j < j1; j++) {
+            const uint2 r = prec[j];
+            s += expf(bufA[r.x & 0xffffu] + __uint_as_float(r.y) + bufB[r.x >> 16] + xn - m);
+          }
+          lg = m + logf(s);
+          gam = expf(lg);
+        }
+        gr[n] = (p.flags & CHAIN_B200_GRAD_AS_LOG) ? lg : gam;
+        gsum += gam;
+      }
+      for (int h = tid; h < S; h += GEN_NT) {
+        const int k0 = fi[2 * h], k1 = fi[2 * h + 1];
+        float m = -INFINITY;
+        for (int k = k0; k < k1; k++) m = fmaxf(m, fp[k] + bufB[ft[3 * k + 1]] + x_s[ft[3 * k + 2]] - tot_t);
+        float v = -INFINITY;
+        if (m > -INFINITY) {
+          float s = 0.f;
+          for (int k = k0; k < k1; k++) s += expf(fp[k] + bufB[ft[3 * k + 1]] + x_s[ft[3 * k + 2]] - tot_t - m);
+          v = m + logf(s);
+        }
+        bufC[h] = v;
+      }
+      if (t == 0 && p.diag) {
+        gsum = block_sum(gsum, scratch);
+        if (tid == 0) { p.diag[2 * b] = 1.f; p.diag[2 * b + 1] = gsum; }
+      }
+    }
+    float *tmp = bufB; bufB = bufC; bufC = tmp;
+    __syncthreads();
+  }
+  if (L == 0 && p.diag && tid == 0) { p.diag[2 * b] = 1.f; p.diag[2 * b + 1] = 1.f; }
+
+  // ------------------------------------------------------------ padded frames
+  {
+    const float fill = (LOG && (p.flags & CHAIN_B200_GRAD_AS_LOG)) ? -INFINITY : 0.f;
+    float *g0 = grad + (size_t)L * D;
+    const size_t n = (size_t)(T - L) * D;
+    for (size_t i = tid; i < n; i += GEN_NT) g0[i] = fill;
+  }
+}
+
+// ---------------------------------------------------------------- finalize
+// objf = sum_b logp[b] (fixed order, double); ok = the reference's t=0 self-check
+// (chain-computation.cc:345-391 / chain-log-domain-computation.cc:283-304).
+__global__ void __launch_bounds__(256) finalize_kernel(const float *__restrict__ logp, const float *__restrict__ diag,
+                                                       int B, int check_ab, float *objf, int32_t *ok,
+                                                       float *diag_out) {
+  __shared__ double sh[3][256];
+  const int tid = threadIdx.x;
+  double a = 0.0, ab = 0.0, gs = 0.0;
+  for (int b = tid; b < B; b += 256) {
+    a += (double)logp[b];
+    ab += (double)diag[2 * b];
+    gs += (double)diag[2 * b + 1];
+  }
+  sh[0][tid] = a; sh[1][tid] = ab; sh[2][tid] = gs;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) { sh[0][tid] += sh[0][tid + o]; sh[1][tid] += sh[1][tid + o]; sh[2][tid] += sh[2][tid + o]; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const float obj = (float)sh[0][0], abp = (float)sh[1][0], gsm = (float)sh[2][0], bsz = (float)B;
+    *objf = obj;
+    int good = 1;
+    // ApproxEqual(a,b,tol) is |a-b| < a*tol (base.cc:6-10); only an excess of 5% clears `ok`
+    if (check_ab && !(fabsf(abp - bsz) < abp * 0.01f) && fabsf(abp - bsz) > 0.05f * bsz) good = 0;
+    if (!(fabsf(gsm - bsz) < gsm * 0.01f) && (fabsf(gsm - bsz) > 0.05f * bsz || gsm - gsm != 0.f)) good = 0;
+    if (!(abp - abp == 0.f) || !(obj - obj == 0.f)) good = 0;  // NaN / inf anywhere
+    *ok = good;
+    if (diag_out) { diag_out[0] = abp; diag_out[1] = gsm; }
+  }
+}
+
+// ---------------------------------------------------------------- host side
+struct GenericWs {
+  size_t alpha, tot, pdf_ptr, pdf_rec, logp, diag, total;
+};
+
+static GenericWs generic_ws_layout(int B, int T, int D, int S, int K, unsigned flags) {
+  GenericWs w;
+  const size_t Bg = (flags & CHAIN_B200_GRAPH_SHARED) ? 1 : (size_t)B;
+  size_t off = 0;
+  w.alpha = off; off = align_up(off + sizeof(float) * (size_t)B * (T + 1) * S);
+  w.tot = off; off = align_up(off + sizeof(float) * (size_t)B * (T + 1));
+  w.pdf_ptr = off; off = align_up(off + sizeof(int32_t) * Bg * (D + 1));
+  w.pdf_rec = off; off = align_up(off + sizeof(uint2) * Bg * (size_t)(K > 0 ? K : 1));
+  w.logp = off; off = align_up(off + sizeof(float) * (size_t)B);
+  w.diag = off; off = align_up(off + sizeof(float) * 2 * (size_t)B);
+  w.total = off;
+  return w;
+}
+
+template <bool LOG>
+static int run_generic(const int32_t *ft, const int32_t *fi, const float *fp, const int32_t *bt, const int32_t *bi,
+                       const float *bp, const float *leaky, const float *init, const float *fin, const float *x,
+                       const int64_t *lengths, int B, int T, int D, int S, int K, float coeff, unsigned flags,
+                       float *objf, float *logp, float *grad, int32_t *ok, float *diag, void *ws, size_t ws_bytes,
+                       int device, void *stream_v) {
+  g_launch_count = 0;
+  if (B <= 0 || T <= 0 || D <= 0 || S <= 0 || K < 0) return CHAIN_B200_ERR_INVALID_ARG;
+  if (!ft || !fi || !fp || !bt || !bi || !bp || !init || !fin || !x || !lengths || !objf || !grad || !ok)
+    return CHAIN_B200_ERR_INVALID_ARG;
+  if (!LOG && !leaky) return CHAIN_B200_ERR_INVALID_ARG;
+  if (!LOG && !(coeff > 0.f && coeff < 1.f)) return CHAIN_B200_ERR_INVALID_ARG;  // chain-computation.cc:68
+  if (S > 65535 || D > 65535) return CHAIN_B200_ERR_UNSUPPORTED;
+  const GenericWs w = generic_ws_layout(B, T, D, S, K, flags);
+  if (!ws || ws_bytes < w.total) return CHAIN_B200_ERR_WORKSPACE;
+  const size_t smem = sizeof(float) * ((size_t)3 * S + D);
+  if (smem > 227 * 1024 - 1024) return CHAIN_B200_ERR_UNSUPPORTED;
+  const size_t sort_smem = sizeof(int) * (size_t)(D + 1);
+
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return (int)guard.err;
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  char *base = (char *)ws;
+  const int Bg = (flags & CHAIN_B200_GRAPH_SHARED) ? 1 : B;
+
+  cudaError_t e;
+  if (sort_smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(pdf_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  pdf_sort_kernel<<<Bg, 128, sort_smem, stream>>>(ft, fi, fp, S, K, D, (int32_t *)(base + w.pdf_ptr),
+                                                 (uint2 *)(base + w.pdf_rec));
+  g_launch_count++;
+
+  GenericParams p;
+  p.ft = ft; p.fi = fi; p.bt = bt; p.bi = bi; p.fp = fp; p.bp = bp;
+  p.leaky = leaky; p.init = init; p.fin = fin; p.x = x; p.lengths = lengths;
+  p.B = B; p.T = T; p.D = D; p.S = S; p.K = K; p.coeff = coeff; p.flags = flags;
+  p.logp = logp ? logp : (float *)(base + w.logp);
+  p.grad = grad;
+  p.diag = (float *)(base + w.diag);
+  p.alpha_ws = (float *)(base + w.alpha);
+  p.tot_ws = (float *)(base + w.tot);
+  p.pdf_ptr = (const int32_t *)(base + w.pdf_ptr);
+  p.pdf_rec = (const uint2 *)(base + w.pdf_rec);
+
+  auto kern = chain_generic_kernel<LOG>;
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  kern<<<B, GEN_NT, smem, stream>>>(p);
+  g_launch_count++;
+  finalize_kernel<<<1, 256, 0, stream>>>(p.logp, p.diag, B, LOG ? 0 : 1, objf, ok, diag);
+  g_launch_count++;
+  e = cudaGetLastError();
+  return (int)e;
+}
+
+}  // namespace chainb200
+
+using namespace chainb200;
+
+extern "C" {
+
+int chain_b200_version(void) { return 100; }
+
+const char *chain_b200_status_string(int status) {
+  switch (status) {
+    case CHAIN_B200_OK: return "ok";
+    case CHAIN_B200_ERR_INVALID_ARG: return "invalid argument";
+    case CHAIN_B200_ERR_WORKSPACE: return "workspace missing or too small";
+    case CHAIN_B200_ERR_UNSUPPORTED: return "graph too large for the on-chip working set (S,D <= 65535; 3S+D floats <= 226 KB)";
+    case CHAIN_B200_ERR_BAD_BLOB: return "not a chain_b200 prepared-graph blob";
+    default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown error";
+  }
+}
+
+void chain_b200_set_verbose_level(int level) { g_verbose_level = level; }
+int chain_b200_get_verbose_level(void) { return g_verbose_level; }
+int chain_b200_last_launch_count(void) { return g_launch_count; }
+
+size_t chain_b200_workspace_bytes(int B, int T, int D, int S, int K, unsigned flags) {
+  if (B <= 0 || T <= 0 || D <= 0 || S <= 0 || K < 0) return 0;
+  return generic_ws_layout(B, T, D, S, K, flags).total;
+}
+
+int chain_b200_forward_backward(const int32_t *ft, const int32_t *fi, const float *fp, const int32_t *bt,
+                                const int32_t *bi, const float *bp, const float *leaky, const float *init,
+                                const float *fin, const float *x, const int64_t *lengths, int B, int T, int D, int S,
+                                int K, float coeff, unsigned flags, float *objf, float *logp, float *grad,
+                                int32_t *ok, float *diag, void *ws, size_t ws_bytes, int device, void *stream) {
+  return run_generic<false>(ft, fi, fp, bt, bi, bp, leaky, init, fin, x, lengths, B, T, D, S, K, coeff, flags, objf,
+                            logp, grad, ok, diag, ws, ws_bytes, device, stream);
+}
+
+int chain_b200_forward_backward_log_domain(const int32_t *ft, const int32_t *fi, const float *fp, const int32_t *bt,
+                                           const int32_t *bi, const float *bp, const float *init, const float *fin,
+                                           const float *x, const int64_t *lengths, int B, int T, int D, int S, int K,
+                                           unsigned flags, float *objf, float *logp, float *grad, int32_t *ok,
+                                           float *diag, void *ws, size_t ws_bytes, int device, void *stream) {
+  return run_generic<true>(ft, fi, fp, bt, bi, bp, nullptr, init, fin, x, lengths, B, T, D, S, K, 0.f,
+                           flags & ~CHAIN_B200_X_IS_EXP, objf, logp, grad, ok, diag, ws, ws_bytes, device, stream);
+}
+
+}  // extern "C"

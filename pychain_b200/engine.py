@@ -1,0 +1,227 @@
+"""Host-side launcher logic above the C ABI (include/chain_b200.h).
+
+PyTorch is used for device memory (outputs, workspace), the current stream and
+nothing else; all arithmetic happens in libchain_b200.so.  There is no CPU path:
+a CPU `x` raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from collections import OrderedDict
+
+import torch
+
+from . import _cabi
+from ._cabi import GRAPH_SHARED, X_IS_EXP, CLAMP_X, GRAD_AS_LOG, ChainB200Error
+
+__all__ = ["forward_backward_prob", "forward_backward_log", "prepare_den_graph", "launch_count", "Result"]
+
+_GRAPH_NAMES_PROB = ("forward_transitions", "forward_transition_indices", "forward_transition_probs",
+                     "backward_transitions", "backward_transition_indices", "backward_transition_probs",
+                     "leaky_probs", "initial_probs", "final_probs")
+_GRAPH_NAMES_LOG = tuple(n for n in _GRAPH_NAMES_PROB if n != "leaky_probs")
+
+# launches issued by this process through the engine (bench.py's gpu_launches)
+_launches = 0
+
+
+def launch_count():
+    return _launches
+
+
+class Result(object):
+    """Outputs of one forward-backward: all device tensors, nothing synchronised."""
+    __slots__ = ("objf", "logp", "grad", "ok", "diag")
+
+    def __init__(self, objf, logp, grad, ok, diag):
+        self.objf, self.logp, self.grad, self.ok, self.diag = objf, logp, grad, ok, diag
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _require_cuda(x, what):
+    if not x.is_cuda:
+        raise ChainB200Error(
+            "{}: nnet output is on '{}'. pychain_b200 is a CUDA (sm_100a) engine with no CPU fallback."
+            .format(what, x.device))
+    if x.dtype != torch.float32:
+        raise ChainB200Error("{}: nnet output must be float32, got {}".format(what, x.dtype))
+    if not x.is_contiguous():
+        raise RuntimeError("{} must be contiguous".format(what))  # CHECK_CONTIGUOUS, pychain.cc:24
+
+
+def _is_shared(tensors, B):
+    """True when every graph tensor is a stride-0 batch view (or B == 1)."""
+    return B == 1 or all(t.stride(0) == 0 for t in tensors)
+
+
+def _graph_to_device(tensors, device, shared, names):
+    """Graph tensors on `device` with the layout the C ABI wants: row 0 only
+    (contiguous) when shared, the contiguous [B,...] batch otherwise."""
+    out = []
+    for t, name in zip(tensors, names):
+        want = torch.int32 if "transition" in name and "probs" not in name else torch.float32
+        if t.dtype != want:
+            raise RuntimeError("{} must be {}, got {}".format(name, want, t.dtype))
+        if shared:
+            t = t[0]
+        elif not t.is_contiguous():
+            raise RuntimeError("{} must be contiguous".format(name))
+        t = t.to(device, non_blocking=True).contiguous()
+        out.append(t)
+    return out
+
+
+# graph tensors already uploaded: key = (data_ptrs, versions, device) -> device tensors.
+# Keeps the per-call `.cuda()` of the reference (chain-computation.cc:77-89) out of the hot path.
+_upload_cache = OrderedDict()
+_UPLOAD_CACHE_MAX = 16
+
+
+def _cached_upload(tensors, device, shared, names):
+    if all(t.is_cuda for t in tensors):
+        return _graph_to_device(tensors, device, shared, names)
+    key = (tuple((t.data_ptr(), t._version, tuple(t.shape), t.stride(0)) for t in tensors), str(device), shared)
+    hit = _upload_cache.get(key)
+    if hit is not None:
+        _upload_cache.move_to_end(key)
+        return hit[1]
+    dev = _graph_to_device(tensors, device, shared, names)
+    _upload_cache[key] = (tensors, dev)  # hold the sources so data_ptr keys stay unique
+    while len(_upload_cache) > _UPLOAD_CACHE_MAX:
+        _upload_cache.popitem(last=False)
+    return dev
+
+
+def _lengths_dev(lengths, device, B):
+    if lengths.numel() != B:
+        raise ValueError("sequence_lengths has {} entries for batch size {}".format(lengths.numel(), B))
+    return lengths.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
+
+
+def _run_generic(log_domain, graph_tensors, x, lengths, num_states, leaky_coefficient, flags, want_logp=True):
+    global _launches
+    lib = _cabi.lib()
+    what = "nnet_output" if log_domain else "exp_nnet_output"
+    _require_cuda(x, what)
+    B, T, D = x.shape
+    names = _GRAPH_NAMES_LOG if log_domain else _GRAPH_NAMES_PROB
+    K = int(graph_tensors[0].size(1))
+    S = int(num_states)
+    shared = _is_shared(graph_tensors, B)
+    if shared:
+        flags |= GRAPH_SHARED
+    dev = x.device
+    g = _cached_upload(list(graph_tensors), dev, shared, names)
+    ldev = _lengths_dev(lengths, dev, B)
+    objf = torch.empty((), dtype=torch.float32, device=dev)
+    logp = torch.empty(B, dtype=torch.float32, device=dev) if want_logp else None
+    grad = torch.empty_like(x)
+    ok = torch.empty(1, dtype=torch.int32, device=dev)
+    diag = torch.empty(2, dtype=torch.float32, device=dev)
+    ws_bytes = lib.chain_b200_workspace_bytes(B, T, D, S, K, flags)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    if log_domain:
+        st = lib.chain_b200_forward_backward_log_domain(
+            *[_ptr(t) for t in g], _ptr(x), _ptr(ldev), B, T, D, S, K, flags,
+            _ptr(objf), _ptr(logp), _ptr(grad), _ptr(ok), _ptr(diag), _ptr(ws), ws_bytes, dev.index or 0, stream)
+        _cabi.check(st, "chain_b200_forward_backward_log_domain")
+    else:
+        st = lib.chain_b200_forward_backward(
+            *[_ptr(t) for t in g], _ptr(x), _ptr(ldev), B, T, D, S, K, float(leaky_coefficient), flags,
+            _ptr(objf), _ptr(logp), _ptr(grad), _ptr(ok), _ptr(diag), _ptr(ws), ws_bytes, dev.index or 0, stream)
+        _cabi.check(st, "chain_b200_forward_backward")
+    _launches += lib.chain_b200_last_launch_count()
+    return Result(objf, logp, grad, ok, diag)
+
+
+# ------------------------------------------------------------------ shared denominator graph
+class PreparedDenGraph(object):
+    """A denominator graph packed once by chain_b200_den_prepare: host blob
+    (launch geometry) + its device copy."""
+
+    def __init__(self, blob_host, blob_dev, S, K, D):
+        self.blob_host, self.blob_dev, self.S, self.K, self.D = blob_host, blob_dev, S, K, D
+
+
+_prepared_cache = OrderedDict()
+
+
+def prepare_den_graph(graph_tensors, num_states, D, device):
+    """Pack (once; cached) a single prob-domain graph given its reference-layout
+    tensors (row 0 of each is used).  `graph_tensors` order = _GRAPH_NAMES_PROB."""
+    lib = _cabi.lib()
+    rows = [t[0] if t.dim() == (3 if "transition" in n and "probs" not in n else 2) else t
+            for t, n in zip(graph_tensors, _GRAPH_NAMES_PROB)]
+    key = (tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in rows), int(D), str(device))
+    hit = _prepared_cache.get(key)
+    if hit is not None:
+        _prepared_cache.move_to_end(key)
+        return hit[1]
+    host = [t.detach().cpu().contiguous() for t in rows]
+    ft, fi, fp, bt, bi, bp, lk, ini, fin = host
+    S, K = int(num_states), int(ft.size(0))
+    nbytes = lib.chain_b200_den_prepare_bytes(_ptr(ft), _ptr(fi), _ptr(bt), _ptr(bi), S, K, int(D))
+    if nbytes < 0:
+        _cabi.check(int(nbytes), "chain_b200_den_prepare_bytes")
+    blob = torch.empty(int(nbytes), dtype=torch.uint8).pin_memory() if torch.cuda.is_available() else \
+        torch.empty(int(nbytes), dtype=torch.uint8)
+    st = lib.chain_b200_den_prepare(*[_ptr(t) for t in host], S, K, int(D), _ptr(blob), int(nbytes))
+    _cabi.check(st, "chain_b200_den_prepare")
+    blob_dev = blob.to(device) if torch.device(device).type == "cuda" else None
+    prep = PreparedDenGraph(blob, blob_dev, S, K, int(D))
+    _prepared_cache[key] = (rows, prep)
+    while len(_prepared_cache) > 8:
+        _prepared_cache.popitem(last=False)
+    return prep
+
+
+def _run_den_shared(prep, x, lengths, leaky_coefficient, flags):
+    global _launches
+    lib = _cabi.lib()
+    _require_cuda(x, "exp_nnet_output" if flags & X_IS_EXP else "nnet_output")
+    B, T, D = x.shape
+    if D != prep.D:
+        raise ValueError("graph was prepared for {} pdfs, input has {}".format(prep.D, D))
+    dev = x.device
+    ldev = _lengths_dev(lengths, dev, B)
+    objf = torch.empty((), dtype=torch.float32, device=dev)
+    logp = torch.empty(B, dtype=torch.float32, device=dev)
+    grad = torch.empty_like(x)
+    ok = torch.empty(1, dtype=torch.int32, device=dev)
+    diag = torch.empty(2, dtype=torch.float32, device=dev)
+    ws_bytes = lib.chain_b200_den_workspace_bytes(_ptr(prep.blob_host), B, T)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    st = lib.chain_b200_den_forward_backward(
+        _ptr(prep.blob_host), _ptr(prep.blob_dev), _ptr(x), _ptr(ldev), B, T, D, float(leaky_coefficient), flags,
+        _ptr(objf), _ptr(logp), _ptr(grad), _ptr(ok), _ptr(diag), _ptr(ws), ws_bytes, dev.index or 0, stream)
+    _cabi.check(st, "chain_b200_den_forward_backward")
+    _launches += lib.chain_b200_last_launch_count()
+    return Result(objf, logp, grad, ok, diag)
+
+
+# ------------------------------------------------------------------ public helpers
+DEN_PATH = "auto"  # "auto": shared graphs use the packed shared-graph kernels; "generic": always the per-sequence kernel
+
+
+def forward_backward_prob(graph_tensors, x, lengths, num_states, leaky_coefficient=1e-5, x_is_exp=True, clamp=False,
+                          path=None):
+    """Probability-domain (denominator) forward-backward.  `graph_tensors` in
+    _GRAPH_NAMES_PROB order, reference layout."""
+    flags = (X_IS_EXP if x_is_exp else 0) | (CLAMP_X if clamp else 0)
+    path = path or DEN_PATH
+    B = x.size(0)
+    if path != "generic" and _is_shared(graph_tensors, B):
+        prep = prepare_den_graph(graph_tensors, num_states, x.size(2), x.device)
+        return _run_den_shared(prep, x, lengths, leaky_coefficient, flags)
+    return _run_generic(False, graph_tensors, x, lengths, num_states, leaky_coefficient, flags)
+
+
+def forward_backward_log(graph_tensors, x, lengths, num_states, grad_as_log=True, clamp=False):
+    """Log-domain (numerator) forward-backward.  `graph_tensors` in _GRAPH_NAMES_LOG order."""
+    flags = (GRAD_AS_LOG if grad_as_log else 0) | (CLAMP_X if clamp else 0)
+    return _run_generic(True, graph_tensors, x, lengths, num_states, 0.0, flags)
