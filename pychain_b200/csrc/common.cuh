@@ -17,6 +17,10 @@ inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a
 extern thread_local int g_launch_count;
 extern int g_verbose_level;
 
+// objf = sum_b logp[b]; ok = the reference's t=0 self-check (defined in generic.cu)
+void launch_finalize(const float *logp, const float *diag, int B, int check_ab, float *objf, int32_t *ok,
+                     float *diag_out, cudaStream_t stream);
+
 struct DeviceGuard {
   int prev = -1;
   bool switched = false;

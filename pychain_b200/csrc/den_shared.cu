@@ -662,9 +662,6 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
   }
 }
 
-// objf / ok reduction (defined in generic.cu)
-__global__ void finalize_kernel(const float *logp, const float *diag, int B, int check_ab, float *objf, int32_t *ok,
-                                float *diag_out);
 
 struct DenWs {
   size_t alpha, tot, logp, diag, total;
@@ -790,7 +787,7 @@ int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev,
   else LAUNCH_DEN(1);
 #undef LAUNCH_DEN
   g_launch_count++;
-  finalize_kernel<<<1, 256, 0, stream>>>(p.logp, p.diag, B, 1, objf, ok, diag);
+  launch_finalize(p.logp, p.diag, B, 1, objf, ok, diag, stream);
   g_launch_count++;
   e = cudaGetLastError();
   return (int)e;

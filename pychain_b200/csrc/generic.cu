@@ -375,6 +375,11 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float *__restrict__
   }
 }
 
+void launch_finalize(const float *logp, const float *diag, int B, int check_ab, float *objf, int32_t *ok,
+                     float *diag_out, cudaStream_t stream) {
+  finalize_kernel<<<1, 256, 0, stream>>>(logp, diag, B, check_ab, objf, ok, diag_out);
+}
+
 // ---------------------------------------------------------------- host side
 struct GenericWs {
   size_t alpha, tot, pdf_ptr, pdf_rec, logp, diag, total;
@@ -447,7 +452,7 @@ static int run_generic(const int32_t *ft, const int32_t *fi, const float *fp, co
   }
   kern<<<B, GEN_NT, smem, stream>>>(p);
   g_launch_count++;
-  finalize_kernel<<<1, 256, 0, stream>>>(p.logp, p.diag, B, LOG ? 0 : 1, objf, ok, diag);
+  launch_finalize(p.logp, p.diag, B, LOG ? 0 : 1, objf, ok, diag, stream);
   g_launch_count++;
   e = cudaGetLastError();
   return (int)e;
