@@ -1,0 +1,51 @@
+// den_blob.h -- layout of a packed shared denominator graph ("blob").
+//
+// The blob is position independent (byte offsets from its start), built on the host by
+// chain_b200_den_prepare (den_pack.cu) and uploaded verbatim.  It holds three sliced-ELL
+// views of the same arc set; in view v every ROW accumulates  sum_k w_k * A[a_k] * B[b_k]:
+//
+//   view 0 (alpha pass)  row = destination state, a = source state (alpha'), b = pdf (x)
+//   view 1 (beta pass)   row = source state,      a = destination  (beta),   b = pdf (x)
+//   view 2 (gamma pass)  row = pdf,               a = source (alpha'),       b = destination (beta)
+//
+// 32 rows form a slice (one row per lane); slices are dealt to the DEN_NW warps of a CTA and
+// each warp's records are stored as ONE contiguous stream in processing order
+// ([slice][k][lane], 8 bytes each: {a:16 | b:16, weight:f32}) followed by kFifoPairs*2
+// null iterations, so the kernel can run a register FIFO of record loads ahead of use
+// without bounds checks.  Slice widths are even (records are consumed in pairs).
+// Rows whose degree exceeds the view's cap are split into sub-rows; a sub-row writes its
+// partial sum to a scratch slot and the listed owner adds the slots up in order.
+#pragma once
+#include <stdint.h>
+
+namespace chainb200 {
+
+constexpr uint32_t kBlobMagic = 0x42324348u;  // "HC2B"
+constexpr uint32_t kBlobVersion = 3;
+constexpr int DEN_NW = 16;           // warps per CTA the slice schedule is built for
+constexpr int DEN_NT = DEN_NW * 32;
+constexpr int kFifoPairs = 3;        // record pairs in flight per lane
+
+struct BlobView {
+  int32_t n_rows, n_slices, n_split, n_sub;
+  int64_t n_recs;
+  int64_t off_rows;         // int32 [n_slices*32]  >= 0 row id; -1 idle lane; <= -2: sub-row slot (-2 - slot)
+  int64_t off_width;        // int32 [n_slices]     even
+  int64_t off_warp_ptr;     // int32 [DEN_NW+1]     range in warp_slices
+  int64_t off_warp_slices;  // int32 [n_slices]     slice ids in each warp's processing order
+  int64_t off_warp_stream;  // int64 [DEN_NW]       record offset of each warp's stream
+  int64_t off_recs;         // uint2 [n_recs]
+  int64_t off_split;        // int32 [n_split*3]    {row, first slot, slot count}
+};
+
+struct BlobHeader {
+  uint32_t magic, version;
+  int32_t S, K, D, nwarps, S_pad, D_pad, max_sub, reserved;
+  BlobView view[3];
+  int64_t off_leaky, off_init, off_final;
+  int64_t total_bytes;
+  double predicted_wavefronts[3];  // packer's bank-conflict model for G=4 (per frame, per CTA)
+  double ideal_wavefronts[3];
+};
+
+}  // namespace chainb200

@@ -1,0 +1,298 @@
+// den_pack.cu -- host-side packer of a shared denominator graph (see den_blob.h).
+//
+// Input: the reference's CSR tensors for ONE graph (produced by
+// /root/reference/openfst_binding/src/fstext.cc:19-117 or by pychain_b200.graph.Fst).
+// Output: the blob consumed by den_shared.cu.  Pure host C++ (no CUDA calls).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+#include "den_blob.h"
+
+namespace chainb200 {
+namespace {
+
+struct Arc {
+  uint32_t ab;  // a | b << 16
+  float w;
+};
+
+struct Unit {            // a row, or one piece of a split row
+  int32_t row_code;      // >= 0 row id; <= -2 sub-row slot
+  std::vector<Arc> arcs;
+};
+
+struct ViewBuild {
+  int n_rows = 0, n_slices = 0, n_split = 0, n_sub = 0;
+  std::vector<int32_t> rows, width, warp_ptr, warp_slices, split;
+  std::vector<int64_t> warp_stream;
+  std::vector<uint32_t> rec_ab;
+  std::vector<float> rec_w;
+  double predicted = 0, ideal = 0;
+};
+
+// Shared-memory wavefronts of one vector gather by a quarter-warp (8 lanes, 16-byte
+// elements => 8 bank groups): the largest number of DISTINCT elements that fall into
+// the same bank group (equal addresses are a broadcast).
+static int quarter_wavefronts(const uint32_t *idx, int n) {
+  int worst = 1;
+  for (int s = 0; s < 8; s++) {
+    uint32_t seen[8];
+    int ns = 0;
+    for (int i = 0; i < n; i++) {
+      if ((idx[i] & 7u) != (uint32_t)s) continue;
+      bool dup = false;
+      for (int j = 0; j < ns; j++) dup |= (seen[j] == idx[i]);
+      if (!dup) seen[ns++] = idx[i];
+    }
+    worst = std::max(worst, ns);
+  }
+  return worst;
+}
+
+// Order the arcs of the 32 units of a slice into columns.  `cols[k][lane]` = index into
+// units[lane].arcs or -1 (idle).  Baseline: the units' own arc order.
+static void arrange_slice(const std::vector<const Unit *> &lanes, int width, std::vector<int> &cols) {
+  cols.assign((size_t)width * 32, -1);
+  for (int l = 0; l < 32; l++) {
+    if (!lanes[l]) continue;
+    const int n = (int)lanes[l]->arcs.size();
+    for (int k = 0; k < n; k++) cols[(size_t)k * 32 + l] = k;
+  }
+}
+
+static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, const std::vector<uint32_t> &ab,
+                       const float *w, int n_a, int n_b, ViewBuild &v) {
+  v.n_rows = n_rows;
+  // rows -> arc lists, arc order inside a row = CSR order (the reference's summation order)
+  std::vector<int32_t> deg(n_rows, 0);
+  for (int k = 0; k < K; k++) deg[row_of[k]]++;
+  std::vector<std::vector<Arc>> by_row(n_rows);
+  for (int r = 0; r < n_rows; r++) by_row[r].reserve(deg[r]);
+  for (int k = 0; k < K; k++) by_row[row_of[k]].push_back(Arc{ab[k], w ? w[k] : 0.f});
+
+  // split heavy rows so that no lane carries more than `cap` arcs
+  const double mean = (double)K / std::max(1, n_rows);
+  int cap = std::max(32, 4 * (int)(mean + 0.999));
+  cap += cap & 1;
+  std::vector<Unit> units;
+  units.reserve(n_rows + 64);
+  v.split.clear();
+  int n_sub = 0;
+  for (int r = 0; r < n_rows; r++) {
+    const int d = deg[r];
+    if (d <= cap) {
+      units.push_back(Unit{r, std::move(by_row[r])});
+      continue;
+    }
+    const int pieces = (d + cap - 1) / cap;
+    v.split.push_back(r); v.split.push_back(n_sub); v.split.push_back(pieces);
+    int pos = 0;
+    for (int pc = 0; pc < pieces; pc++) {
+      const int len = d / pieces + (pc < d % pieces ? 1 : 0);
+      Unit u;
+      u.row_code = -2 - (n_sub++);
+      u.arcs.assign(by_row[r].begin() + pos, by_row[r].begin() + pos + len);
+      pos += len;
+      units.push_back(std::move(u));
+    }
+  }
+  v.n_split = (int)v.split.size() / 3;
+  v.n_sub = n_sub;
+
+  // longest first, 32 units per slice
+  std::vector<int> order(units.size());
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(),
+                   [&](int x, int y) { return units[x].arcs.size() > units[y].arcs.size(); });
+  const int n_slices = ((int)units.size() + 31) / 32;
+  v.n_slices = n_slices;
+  v.rows.assign((size_t)n_slices * 32, -1);
+  v.width.assign(n_slices, 0);
+  std::vector<std::vector<uint32_t>> s_ab(n_slices);
+  std::vector<std::vector<float>> s_w(n_slices);
+  const uint32_t na = (uint32_t)n_a, nb = (uint32_t)n_b;
+  for (int s = 0; s < n_slices; s++) {
+    std::vector<const Unit *> lanes(32, nullptr);
+    int width = 0;
+    for (int l = 0; l < 32; l++) {
+      const size_t i = (size_t)s * 32 + l;
+      if (i >= units.size()) break;
+      lanes[l] = &units[order[i]];
+      v.rows[i] = lanes[l]->row_code;
+      width = std::max(width, (int)lanes[l]->arcs.size());
+    }
+    width += width & 1;
+    std::vector<int> cols;
+    arrange_slice(lanes, width, cols);
+    width = (int)(cols.size() / 32);
+    v.width[s] = width;
+    s_ab[s].assign((size_t)width * 32, 0u);
+    s_w[s].assign((size_t)width * 32, 0.f);
+    for (int k = 0; k < width; k++) {
+      uint32_t ia[32], ib[32];
+      for (int l = 0; l < 32; l++) {
+        const int j = cols[(size_t)k * 32 + l];
+        uint32_t rec;
+        float wt = 0.f;
+        if (j >= 0) {
+          rec = lanes[l]->arcs[j].ab;
+          wt = lanes[l]->arcs[j].w;
+        } else {  // idle lane: weight 0; index = the lane's own bank group so idle lanes never collide
+          const uint32_t q = (uint32_t)(l & 7);
+          rec = (q < na ? q : 0u) | ((q < nb ? q : 0u) << 16);
+        }
+        s_ab[s][(size_t)k * 32 + l] = rec;
+        s_w[s][(size_t)k * 32 + l] = wt;
+        ia[l] = rec & 0xffffu;
+        ib[l] = rec >> 16;
+      }
+      for (int q = 0; q < 4; q++) {
+        v.predicted += quarter_wavefronts(ia + 8 * q, 8) + quarter_wavefronts(ib + 8 * q, 8);
+        v.ideal += 2;
+      }
+    }
+  }
+
+  // slices -> warps: longest-processing-time first (slices are sorted by width already)
+  std::vector<long> load(DEN_NW, 0);
+  std::vector<std::vector<int32_t>> per(DEN_NW);
+  for (int s = 0; s < n_slices; s++) {
+    int best = 0;
+    for (int wv = 1; wv < DEN_NW; wv++)
+      if (load[wv] < load[best]) best = wv;
+    per[best].push_back(s);
+    load[best] += v.width[s] + 4;
+  }
+  v.warp_ptr.assign(DEN_NW + 1, 0);
+  v.warp_slices.clear();
+  v.warp_stream.assign(DEN_NW, 0);
+  v.rec_ab.clear();
+  v.rec_w.clear();
+  for (int wv = 0; wv < DEN_NW; wv++) {
+    v.warp_ptr[wv + 1] = v.warp_ptr[wv] + (int32_t)per[wv].size();
+    v.warp_stream[wv] = (int64_t)v.rec_ab.size();
+    for (int s : per[wv]) {
+      v.warp_slices.push_back(s);
+      v.rec_ab.insert(v.rec_ab.end(), s_ab[s].begin(), s_ab[s].end());
+      v.rec_w.insert(v.rec_w.end(), s_w[s].begin(), s_w[s].end());
+    }
+    v.rec_ab.insert(v.rec_ab.end(), (size_t)kFifoPairs * 2 * 32, 0u);  // FIFO run-out
+    v.rec_w.insert(v.rec_w.end(), (size_t)kFifoPairs * 2 * 32, 0.f);
+  }
+}
+
+}  // namespace
+
+int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, const int32_t *bt, const int32_t *bi,
+                      const float *bp, const float *leaky, const float *init, const float *fin, int S, int K, int D,
+                      void *out, int64_t out_bytes) {
+  if (S <= 0 || K <= 0 || D <= 0 || !ft || !fi || !bt || !bi) return CHAIN_B200_ERR_INVALID_ARG;
+  if (S > 65535 || D > 65535) return CHAIN_B200_ERR_UNSUPPORTED;
+  // validate the CSR: contiguous coverage, indices in range, rows grouped as claimed
+  int kf = 0, kb = 0;
+  for (int s = 0; s < S; s++) {
+    if (fi[2 * s] != kf || fi[2 * s + 1] < kf || fi[2 * s + 1] > K) return CHAIN_B200_ERR_INVALID_ARG;
+    kf = fi[2 * s + 1];
+    if (bi[2 * s] != kb || bi[2 * s + 1] < kb || bi[2 * s + 1] > K) return CHAIN_B200_ERR_INVALID_ARG;
+    kb = bi[2 * s + 1];
+  }
+  if (kf != kb || kf <= 0) return CHAIN_B200_ERR_INVALID_ARG;
+  const int Kv = kf;  // real arcs (entries beyond are batch padding)
+  for (int s = 0; s < S; s++) {
+    for (int k = bi[2 * s]; k < bi[2 * s + 1]; k++)
+      if (bt[3 * k + 1] != s) return CHAIN_B200_ERR_INVALID_ARG;
+    for (int k = fi[2 * s]; k < fi[2 * s + 1]; k++)
+      if (ft[3 * k] != s) return CHAIN_B200_ERR_INVALID_ARG;
+  }
+  std::vector<int32_t> row_dst(Kv), row_src(Kv), row_pdf(Kv);
+  std::vector<uint32_t> ab_fwd(Kv), ab_bwd(Kv), ab_gam(Kv);
+  for (int k = 0; k < Kv; k++) {
+    const int32_t bs = bt[3 * k], bd = bt[3 * k + 1], bn = bt[3 * k + 2];
+    const int32_t fs = ft[3 * k], fd = ft[3 * k + 1], fn = ft[3 * k + 2];
+    if (bs < 0 || bs >= S || bd < 0 || bd >= S || bn < 0 || bn >= D) return CHAIN_B200_ERR_INVALID_ARG;
+    if (fs < 0 || fs >= S || fd < 0 || fd >= S || fn < 0 || fn >= D) return CHAIN_B200_ERR_INVALID_ARG;
+    row_dst[k] = bd; ab_fwd[k] = (uint32_t)bs | ((uint32_t)bn << 16);  // backward-CSR order
+    row_src[k] = fs; ab_bwd[k] = (uint32_t)fd | ((uint32_t)fn << 16);  // forward-CSR order
+    row_pdf[k] = fn; ab_gam[k] = (uint32_t)fs | ((uint32_t)fd << 16);  // forward-CSR order
+  }
+  ViewBuild vb[3];
+  build_view(S, Kv, row_dst, ab_fwd, bp, S, D, vb[0]);
+  build_view(S, Kv, row_src, ab_bwd, fp, S, D, vb[1]);
+  build_view(D, Kv, row_pdf, ab_gam, fp, S, S, vb[2]);
+
+  BlobHeader h;
+  memset(&h, 0, sizeof(h));
+  h.magic = kBlobMagic; h.version = kBlobVersion;
+  h.S = S; h.K = Kv; h.D = D; h.nwarps = DEN_NW;
+  h.S_pad = (S + 3) / 4 * 4; h.D_pad = (D + 3) / 4 * 4;
+  size_t off = align_up(sizeof(BlobHeader));
+  for (int i = 0; i < 3; i++) {
+    BlobView &bv = h.view[i];
+    const ViewBuild &b = vb[i];
+    bv.n_rows = b.n_rows; bv.n_slices = b.n_slices; bv.n_split = b.n_split; bv.n_sub = b.n_sub;
+    bv.n_recs = (int64_t)b.rec_ab.size();
+    h.max_sub = std::max(h.max_sub, b.n_sub);
+    h.predicted_wavefronts[i] = b.predicted;
+    h.ideal_wavefronts[i] = b.ideal;
+    bv.off_rows = (int64_t)off; off = align_up(off + b.rows.size() * 4);
+    bv.off_width = (int64_t)off; off = align_up(off + b.width.size() * 4);
+    bv.off_warp_ptr = (int64_t)off; off = align_up(off + b.warp_ptr.size() * 4);
+    bv.off_warp_slices = (int64_t)off; off = align_up(off + b.warp_slices.size() * 4 + 4);
+    bv.off_warp_stream = (int64_t)off; off = align_up(off + b.warp_stream.size() * 8);
+    bv.off_recs = (int64_t)off; off = align_up(off + b.rec_ab.size() * 8 + 8);
+    bv.off_split = (int64_t)off; off = align_up(off + b.split.size() * 4 + 4);
+  }
+  h.off_leaky = (int64_t)off; off = align_up(off + (size_t)h.S_pad * 4);
+  h.off_init = (int64_t)off; off = align_up(off + (size_t)h.S_pad * 4);
+  h.off_final = (int64_t)off; off = align_up(off + (size_t)h.S_pad * 4);
+  h.total_bytes = (int64_t)off;
+  if (!out) return h.total_bytes;
+  if (out_bytes < h.total_bytes || !fp || !bp || !leaky || !init || !fin) return CHAIN_B200_ERR_INVALID_ARG;
+  char *base = (char *)out;
+  memset(base, 0, (size_t)h.total_bytes);
+  memcpy(base, &h, sizeof(h));
+  for (int i = 0; i < 3; i++) {
+    const BlobView &bv = h.view[i];
+    const ViewBuild &b = vb[i];
+    memcpy(base + bv.off_rows, b.rows.data(), b.rows.size() * 4);
+    memcpy(base + bv.off_width, b.width.data(), b.width.size() * 4);
+    memcpy(base + bv.off_warp_ptr, b.warp_ptr.data(), b.warp_ptr.size() * 4);
+    memcpy(base + bv.off_warp_slices, b.warp_slices.data(), b.warp_slices.size() * 4);
+    memcpy(base + bv.off_warp_stream, b.warp_stream.data(), b.warp_stream.size() * 8);
+    memcpy(base + bv.off_split, b.split.data(), b.split.size() * 4);
+    uint32_t *rec = (uint32_t *)(base + bv.off_recs);
+    for (size_t j = 0; j < b.rec_ab.size(); j++) {
+      rec[2 * j] = b.rec_ab[j];
+      memcpy(&rec[2 * j + 1], &b.rec_w[j], 4);
+    }
+  }
+  memcpy(base + h.off_leaky, leaky, (size_t)S * 4);
+  memcpy(base + h.off_init, init, (size_t)S * 4);
+  memcpy(base + h.off_final, fin, (size_t)S * 4);
+  return h.total_bytes;
+}
+
+}  // namespace chainb200
+
+using namespace chainb200;
+
+extern "C" {
+
+int64_t chain_b200_den_prepare_bytes(const int32_t *ft, const int32_t *fi, const int32_t *bt, const int32_t *bi, int S,
+                                     int K, int D) {
+  return pack_den_blob(ft, fi, nullptr, bt, bi, nullptr, nullptr, nullptr, nullptr, S, K, D, nullptr, 0);
+}
+
+int chain_b200_den_prepare(const int32_t *ft, const int32_t *fi, const float *fp, const int32_t *bt,
+                           const int32_t *bi, const float *bp, const float *leaky, const float *init,
+                           const float *fin, int S, int K, int D, void *blob, int64_t blob_bytes) {
+  if (!blob) return CHAIN_B200_ERR_INVALID_ARG;
+  const int64_t r = pack_den_blob(ft, fi, fp, bt, bi, bp, leaky, init, fin, S, K, D, blob, blob_bytes);
+  return r < 0 ? (int)r : CHAIN_B200_OK;
+}
+
+}  // extern "C"

@@ -26,195 +26,18 @@
 //    and the zeroing of padded frames are all inside the one kernel.
 #include <algorithm>
 #include <cstdlib>
-#include <cstring>
-#include <numeric>
-#include <vector>
 
 #include "common.cuh"
+#include "den_blob.h"
 
 namespace chainb200 {
 
-constexpr uint32_t kBlobMagic = 0x42324348u;  // "HC2B"
-constexpr uint32_t kBlobVersion = 2;
-constexpr int DEN_NW = 16;
-constexpr int DEN_NT = DEN_NW * 32;
-
-struct BlobView {
-  int32_t n_rows, n_slices;
-  int64_t n_recs;
-  int64_t off_rows;         // int32 [n_slices*32]  row id per (slice, lane), -1 = padding lane
-  int64_t off_desc;         // int2  [n_slices]     {record offset, width}
-  int64_t off_warp_ptr;     // int32 [nwarps+1]
-  int64_t off_warp_slices;  // int32 [n_slices]     slice ids grouped by warp
-  int64_t off_recs;         // uint2 [n_recs]
-};
-
-struct BlobHeader {
-  uint32_t magic, version;
-  int32_t S, K, D, nwarps, S_pad, D_pad;
-  BlobView view[3];  // 0: by destination (alpha), 1: by source (beta), 2: by pdf (gamma)
-  int64_t off_leaky, off_init, off_final;
-  int64_t total_bytes;
-};
-
-// ------------------------------------------------------------------------------- host: packing
-namespace {
-
-struct ViewBuild {
-  std::vector<int32_t> rows, warp_ptr, warp_slices;
-  std::vector<int32_t> desc;  // 2 per slice
-  std::vector<uint32_t> rec_idx;  // a | b << 16
-  std::vector<float> rec_w;
-};
-
-// row_of[k]: key row of arc k; arcs are visited in index order (the CSR order of `trans`).
-static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, const std::vector<uint32_t> &ab,
-                       const float *w, int nwarps, ViewBuild &v) {
-  std::vector<int32_t> deg(n_rows, 0);
-  for (int k = 0; k < K; k++) deg[row_of[k]]++;
-  std::vector<int32_t> start(n_rows + 1, 0);
-  for (int r = 0; r < n_rows; r++) start[r + 1] = start[r] + deg[r];
-  std::vector<int32_t> arcs(K), fill(start.begin(), start.end() - 1);
-  for (int k = 0; k < K; k++) arcs[fill[row_of[k]]++] = k;  // stable: arc order inside a row is preserved
-  std::vector<int32_t> order(n_rows);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return deg[a] > deg[b]; });
-  const int n_slices = (n_rows + 31) / 32;
-  v.rows.assign((size_t)n_slices * 32, -1);
-  v.desc.assign((size_t)n_slices * 2, 0);
-  size_t n_recs = 0;
-  for (int s = 0; s < n_slices; s++) {
-    int width = 0;
-    for (int l = 0; l < 32; l++) {
-      const int i = s * 32 + l;
-      if (i < n_rows) { v.rows[i] = order[i]; width = std::max(width, deg[order[i]]); }
-    }
-    v.desc[2 * s] = (int32_t)n_recs;
-    v.desc[2 * s + 1] = width;
-    n_recs += (size_t)width * 32;
-  }
-  v.rec_idx.assign(n_recs, 0u);
-  v.rec_w.assign(n_recs, 0.f);
-  for (int s = 0; s < n_slices; s++) {
-    const int off = v.desc[2 * s], width = v.desc[2 * s + 1];
-    for (int l = 0; l < 32; l++) {
-      const int r = v.rows[(size_t)s * 32 + l];
-      if (r < 0) continue;
-      for (int j = 0; j < deg[r] && j < width; j++) {
-        const int k = arcs[start[r] + j];
-        v.rec_idx[(size_t)off + (size_t)j * 32 + l] = ab[k];
-        v.rec_w[(size_t)off + (size_t)j * 32 + l] = w ? w[k] : 0.f;
-      }
-    }
-  }
-  // slices -> warps: longest-processing-time first (slices are already sorted by width)
-  std::vector<long> load(nwarps, 0);
-  std::vector<std::vector<int32_t>> per(nwarps);
-  for (int s = 0; s < n_slices; s++) {
-    int best = 0;
-    for (int wv = 1; wv < nwarps; wv++)
-      if (load[wv] < load[best]) best = wv;
-    per[best].push_back(s);
-    load[best] += v.desc[2 * s + 1] + 3;
-  }
-  v.warp_ptr.assign(nwarps + 1, 0);
-  v.warp_slices.clear();
-  for (int wv = 0; wv < nwarps; wv++) {
-    v.warp_ptr[wv + 1] = v.warp_ptr[wv] + (int32_t)per[wv].size();
-    v.warp_slices.insert(v.warp_slices.end(), per[wv].begin(), per[wv].end());
-  }
-}
-
-static int64_t pack_blob(const int32_t *ft, const int32_t *fi, const float *fp, const int32_t *bt, const int32_t *bi,
-                         const float *bp, const float *leaky, const float *init, const float *fin, int S, int K, int D,
-                         void *out, int64_t out_bytes) {
-  if (S <= 0 || K <= 0 || D <= 0 || !ft || !fi || !bt || !bi) return CHAIN_B200_ERR_INVALID_ARG;
-  if (S > 65535 || D > 65535) return CHAIN_B200_ERR_UNSUPPORTED;
-  // validate the CSR: full coverage, indices in range
-  int kf = 0, kb = 0;
-  for (int s = 0; s < S; s++) {
-    if (fi[2 * s] != kf || fi[2 * s + 1] < kf || fi[2 * s + 1] > K) return CHAIN_B200_ERR_INVALID_ARG;
-    kf = fi[2 * s + 1];
-    if (bi[2 * s] != kb || bi[2 * s + 1] < kb || bi[2 * s + 1] > K) return CHAIN_B200_ERR_INVALID_ARG;
-    kb = bi[2 * s + 1];
-  }
-  if (kf != kb) return CHAIN_B200_ERR_INVALID_ARG;
-  const int Kv = kf;  // real arcs (rows beyond are padding)
-  std::vector<int32_t> row_dst(Kv), row_src(Kv), row_pdf(Kv);
-  std::vector<uint32_t> ab_fwd(Kv), ab_bwd(Kv), ab_gam(Kv);
-  for (int s = 0; s < S; s++)
-    for (int k = bi[2 * s]; k < bi[2 * s + 1]; k++)
-      if (bt[3 * k + 1] != s) return CHAIN_B200_ERR_INVALID_ARG;
-  for (int s = 0; s < S; s++)
-    for (int k = fi[2 * s]; k < fi[2 * s + 1]; k++)
-      if (ft[3 * k] != s) return CHAIN_B200_ERR_INVALID_ARG;
-  for (int k = 0; k < Kv; k++) {
-    const int32_t bs = bt[3 * k], bd = bt[3 * k + 1], bn = bt[3 * k + 2];
-    const int32_t fs = ft[3 * k], fd = ft[3 * k + 1], fn = ft[3 * k + 2];
-    if (bs < 0 || bs >= S || bd < 0 || bd >= S || bn < 0 || bn >= D) return CHAIN_B200_ERR_INVALID_ARG;
-    if (fs < 0 || fs >= S || fd < 0 || fd >= S || fn < 0 || fn >= D) return CHAIN_B200_ERR_INVALID_ARG;
-    row_dst[k] = bd; ab_fwd[k] = (uint32_t)bs | ((uint32_t)bn << 16);  // alpha pass: a = src, b = pdf (backward CSR order)
-    row_src[k] = fs; ab_bwd[k] = (uint32_t)fd | ((uint32_t)fn << 16);  // beta pass:  a = dst, b = pdf (forward CSR order)
-    row_pdf[k] = fn; ab_gam[k] = (uint32_t)fs | ((uint32_t)fd << 16);  // gamma pass: a = src, b = dst (forward CSR order)
-  }
-  ViewBuild vb[3];
-  build_view(S, Kv, row_dst, ab_fwd, bp, DEN_NW, vb[0]);
-  build_view(S, Kv, row_src, ab_bwd, fp, DEN_NW, vb[1]);
-  build_view(D, Kv, row_pdf, ab_gam, fp, DEN_NW, vb[2]);
-
-  BlobHeader h;
-  memset(&h, 0, sizeof(h));
-  h.magic = kBlobMagic; h.version = kBlobVersion;
-  h.S = S; h.K = Kv; h.D = D; h.nwarps = DEN_NW;
-  h.S_pad = (S + 3) / 4 * 4; h.D_pad = (D + 3) / 4 * 4;
-  size_t off = align_up(sizeof(BlobHeader));
-  for (int i = 0; i < 3; i++) {
-    BlobView &bv = h.view[i];
-    bv.n_rows = (i == 2) ? D : S;
-    bv.n_slices = (int32_t)(vb[i].rows.size() / 32);
-    bv.n_recs = (int64_t)vb[i].rec_idx.size();
-    bv.off_rows = (int64_t)off; off = align_up(off + vb[i].rows.size() * 4);
-    bv.off_desc = (int64_t)off; off = align_up(off + vb[i].desc.size() * 4);
-    bv.off_warp_ptr = (int64_t)off; off = align_up(off + vb[i].warp_ptr.size() * 4);
-    bv.off_warp_slices = (int64_t)off; off = align_up(off + vb[i].warp_slices.size() * 4 + 4);
-    bv.off_recs = (int64_t)off; off = align_up(off + vb[i].rec_idx.size() * 8 + 8);
-  }
-  h.off_leaky = (int64_t)off; off = align_up(off + (size_t)h.S_pad * 4);
-  h.off_init = (int64_t)off; off = align_up(off + (size_t)h.S_pad * 4);
-  h.off_final = (int64_t)off; off = align_up(off + (size_t)h.S_pad * 4);
-  h.total_bytes = (int64_t)off;
-  if (!out) return h.total_bytes;
-  if (out_bytes < h.total_bytes || !fp || !bp || !leaky || !init || !fin) return CHAIN_B200_ERR_INVALID_ARG;
-  char *base = (char *)out;
-  memset(base, 0, (size_t)h.total_bytes);
-  memcpy(base, &h, sizeof(h));
-  for (int i = 0; i < 3; i++) {
-    const BlobView &bv = h.view[i];
-    memcpy(base + bv.off_rows, vb[i].rows.data(), vb[i].rows.size() * 4);
-    memcpy(base + bv.off_desc, vb[i].desc.data(), vb[i].desc.size() * 4);
-    memcpy(base + bv.off_warp_ptr, vb[i].warp_ptr.data(), vb[i].warp_ptr.size() * 4);
-    memcpy(base + bv.off_warp_slices, vb[i].warp_slices.data(), vb[i].warp_slices.size() * 4);
-    uint32_t *rec = (uint32_t *)(base + bv.off_recs);
-    for (size_t j = 0; j < vb[i].rec_idx.size(); j++) {
-      rec[2 * j] = vb[i].rec_idx[j];
-      memcpy(&rec[2 * j + 1], &vb[i].rec_w[j], 4);
-    }
-  }
-  memcpy(base + h.off_leaky, leaky, (size_t)S * 4);
-  memcpy(base + h.off_init, init, (size_t)S * 4);
-  memcpy(base + h.off_final, fin, (size_t)S * 4);
-  return h.total_bytes;
-}
-
-}  // namespace
-
 // ------------------------------------------------------------------------------- device
 struct DView {
-  const int32_t *rows;
-  const int2 *desc;
-  const int32_t *warp_ptr;
-  const int32_t *warp_slices;
+  const int32_t *rows, *width, *warp_ptr, *warp_slices, *split;
+  const int64_t *warp_stream;
   const uint2 *recs;
+  int n_split;
 };
 
 struct DenParams {
@@ -287,43 +110,68 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// One SELL pass: every lane owns one row of each of its warp's slices and
-// accumulates sum_k w_k * A[a_k][g] * Bv[b_k][g] over the row's records.
+template <int G>
+__device__ __forceinline__ void consume_rec(const uint2 r, const float *__restrict__ A, const float *__restrict__ Bv,
+                                            float (&acc)[G]) {
+  float a[G], b[G];
+  ld_vec<G>(A + (r.x & 0xffffu) * G, a);
+  ld_vec<G>(Bv + (r.x >> 16) * G, b);
+  const float w = __uint_as_float(r.y);
+#pragma unroll
+  for (int g = 0; g < G; g++) acc[g] = fmaf(a[g] * w, b[g], acc[g]);
+}
+
+// One SELL pass: every lane owns one row (or sub-row) of each of its warp's slices and
+// accumulates sum_k w_k * A[a_k][g] * Bv[b_k][g] over the row's records.  The warp's
+// records are one contiguous stream; a register FIFO keeps kFifoPairs pairs of record
+// loads (L2 latency) in flight ahead of their use, across slice boundaries.
 template <int G, class Epi>
 __device__ __forceinline__ void sell_pass(const DView &v, const float *__restrict__ A, const float *__restrict__ Bv,
-                                          int warp, int lane, Epi epi) {
+                                          float *__restrict__ partial, int warp, int lane, Epi &epi) {
+  const uint2 *sp = v.recs + v.warp_stream[warp] + lane;
+  uint2 f[kFifoPairs][2];
+#pragma unroll
+  for (int d = 0; d < kFifoPairs; d++) {
+    f[d][0] = ldg_stream(sp + (2 * d) * 32);
+    f[d][1] = ldg_stream(sp + (2 * d + 1) * 32);
+  }
+  sp += 2 * kFifoPairs * 32;
   const int s1 = v.warp_ptr[warp + 1];
   for (int si = v.warp_ptr[warp]; si < s1; si++) {
     const int slice = v.warp_slices[si];
-    const int2 d = __ldg(&v.desc[slice]);
+    const int w = __ldg(&v.width[slice]);
     const int row = __ldg(&v.rows[slice * 32 + lane]);
-    const uint2 *rp = v.recs + d.x + lane;
     float acc[G];
 #pragma unroll
     for (int g = 0; g < G; g++) acc[g] = 0.f;
-    int k = 0;
-    for (; k + 4 <= d.y; k += 4) {
-      uint2 r[4];
+    for (int k = 0; k < w; k += 2) {
+      const uint2 r0 = f[0][0], r1 = f[0][1];
 #pragma unroll
-      for (int u = 0; u < 4; u++) r[u] = ldg_stream(rp + (k + u) * 32);
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        float a[G], b[G];
-        ld_vec<G>(A + (r[u].x & 0xffffu) * G, a);
-        ld_vec<G>(Bv + (r[u].x >> 16) * G, b);
-        const float w = __uint_as_float(r[u].y);
-#pragma unroll
-        for (int g = 0; g < G; g++) acc[g] = fmaf(a[g] * w, b[g], acc[g]);
-      }
+      for (int d = 0; d + 1 < kFifoPairs; d++) { f[d][0] = f[d + 1][0]; f[d][1] = f[d + 1][1]; }
+      f[kFifoPairs - 1][0] = ldg_stream(sp);
+      f[kFifoPairs - 1][1] = ldg_stream(sp + 32);
+      sp += 64;
+      consume_rec<G>(r0, A, Bv, acc);
+      consume_rec<G>(r1, A, Bv, acc);
     }
-    for (; k < d.y; k++) {
-      const uint2 r = ldg_stream(rp + k * 32);
-      float a[G], b[G];
-      ld_vec<G>(A + (r.x & 0xffffu) * G, a);
-      ld_vec<G>(Bv + (r.x >> 16) * G, b);
-      const float w = __uint_as_float(r.y);
+    if (row >= 0) epi(row, acc);
+    else if (row <= -2) st_vec<G>(partial + (size_t)(-2 - row) * G, acc);
+  }
+}
+
+// Rows that were split: add the sub-row partial sums (fixed order) and run the epilogue.
+template <int G, class Epi>
+__device__ __forceinline__ void fixup_split(const DView &v, const float *__restrict__ partial, Epi &epi) {
+  for (int i = threadIdx.x; i < v.n_split; i += DEN_NT) {
+    const int row = v.split[3 * i], first = v.split[3 * i + 1], cnt = v.split[3 * i + 2];
+    float acc[G];
 #pragma unroll
-      for (int g = 0; g < G; g++) acc[g] = fmaf(a[g] * w, b[g], acc[g]);
+    for (int g = 0; g < G; g++) acc[g] = 0.f;
+    for (int j = 0; j < cnt; j++) {
+      float t[G];
+      ld_vec<G>(partial + (size_t)(first + j) * G, t);
+#pragma unroll
+      for (int g = 0; g < G; g++) acc[g] += t[g];
     }
     epi(row, acc);
   }
@@ -363,6 +211,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
   float *x_s = buf1 + (size_t)S_pad * G;
   float *xraw = x_s + (size_t)D_pad * G;
   float *gam_s = xraw + (size_t)D_pad * G;
+  float *partial = gam_s + (size_t)D_pad * G;
   const float *__restrict__ lk = p.leaky;
   const float *__restrict__ ini = p.init;
   const float *__restrict__ fin = p.fin;
@@ -483,14 +332,14 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       float inv[G], part[G];
 #pragma unroll
       for (int g = 0; g < G; g++) { inv[g] = tot[g] > 0.f ? 1.0f / tot[g] : 0.f; part[g] = 0.f; }
-      sell_pass<G>(p.view[0], A, x_s, warp, lane, [&](int row, const float (&acc)[G]) {
-        if (row >= 0) {
-          float o[G];
+      auto epi_fwd = [&](int row, const float (&acc)[G]) {
+        float o[G];
 #pragma unroll
-          for (int g = 0; g < G; g++) { o[g] = acc[g] * inv[g]; part[g] += o[g]; }
-          st_vec<G>(Bn + (size_t)row * G, o);
-        }
-      });
+        for (int g = 0; g < G; g++) { o[g] = acc[g] * inv[g]; part[g] += o[g]; }
+        st_vec<G>(Bn + (size_t)row * G, o);
+      };
+      sell_pass<G>(p.view[0], A, x_s, partial, warp, lane, epi_fwd);
+      if (p.view[0].n_split) { __syncthreads(); fixup_split<G>(p.view[0], partial, epi_fwd); }
 #pragma unroll
       for (int g = 0; g < G; g++) {
         part[g] = warp_sum(part[g]);
@@ -581,36 +430,36 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       float gsum[G];
 #pragma unroll
       for (int g = 0; g < G; g++) gsum[g] = 0.f;
-      sell_pass<G>(p.view[2], P, Q, warp, lane, [&](int row, const float (&acc)[G]) {
-        if (row >= 0) {
-          float xv[G], o[G];
-          ld_vec<G>(x_s + (size_t)row * G, xv);
+      auto epi_gam = [&](int row, const float (&acc)[G]) {
+        float xv[G], o[G];
+        ld_vec<G>(x_s + (size_t)row * G, xv);
 #pragma unroll
-          for (int g = 0; g < G; g++) { o[g] = acc[g] * xv[g] * inv[g]; gsum[g] += o[g]; }
-          st_vec<G>(gam_s + (size_t)row * G, o);
-        }
-      });
+        for (int g = 0; g < G; g++) { o[g] = acc[g] * xv[g] * inv[g]; gsum[g] += o[g]; }
+        st_vec<G>(gam_s + (size_t)row * G, o);
+      };
+      sell_pass<G>(p.view[2], P, Q, partial, warp, lane, epi_gam);
+      if (p.view[2].n_split) { __syncthreads(); fixup_split<G>(p.view[2], partial, epi_gam); }
       __syncthreads();  // gamma rows complete; everybody done reading P
 
       // ---- beta' pass: rows = source states; beta'(t,i) = sum p beta(t+1,dst) x(t,pdf) / tot(t)
       float lpart[G], ab[G];
 #pragma unroll
       for (int g = 0; g < G; g++) { lpart[g] = 0.f; ab[g] = 0.f; }
-      sell_pass<G>(p.view[1], Q, x_s, warp, lane, [&](int row, const float (&acc)[G]) {
-        if (row >= 0) {
-          float o[G];
-          const float l = __ldg(lk + row);
-          if (t == 0) {
-            float av[G];
-            ld_vec<G>(P + (size_t)row * G, av);
+      auto epi_bwd = [&](int row, const float (&acc)[G]) {
+        float o[G];
+        const float l = __ldg(lk + row);
+        if (t == 0) {
+          float av[G];
+          ld_vec<G>(P + (size_t)row * G, av);
 #pragma unroll
-            for (int g = 0; g < G; g++) ab[g] = fmaf(av[g], acc[g] * inv[g], ab[g]);
-          }
-#pragma unroll
-          for (int g = 0; g < G; g++) { o[g] = acc[g] * inv[g]; lpart[g] = fmaf(o[g], l, lpart[g]); }
-          st_vec<G>(P + (size_t)row * G, o);
+          for (int g = 0; g < G; g++) ab[g] = fmaf(av[g], acc[g] * inv[g], ab[g]);
         }
-      });
+#pragma unroll
+        for (int g = 0; g < G; g++) { o[g] = acc[g] * inv[g]; lpart[g] = fmaf(o[g], l, lpart[g]); }
+        st_vec<G>(P + (size_t)row * G, o);
+      };
+      sell_pass<G>(p.view[1], Q, x_s, partial, warp, lane, epi_bwd);
+      if (p.view[1].n_split) { __syncthreads(); fixup_split<G>(p.view[1], partial, epi_bwd); }
 #pragma unroll
       for (int g = 0; g < G; g++) {
         lpart[g] = warp_sum(lpart[g]);
@@ -679,7 +528,7 @@ static DenWs den_ws_layout(const BlobHeader &h, int B, int T) {
 }
 
 static size_t den_smem_bytes(const BlobHeader &h, int G) {
-  return sizeof(float) * ((size_t)2 * h.S_pad * G + (size_t)3 * h.D_pad * G) + 128;
+  return sizeof(float) * ((size_t)2 * h.S_pad * G + (size_t)3 * h.D_pad * G + (size_t)h.max_sub * G) + 128;
 }
 
 // Relative cost of one frame for a group of G utterances (shared-memory wavefronts of
@@ -707,19 +556,6 @@ static int choose_G(const BlobHeader &h, int B, int num_sms) {
 using namespace chainb200;
 
 extern "C" {
-
-int64_t chain_b200_den_prepare_bytes(const int32_t *ft, const int32_t *fi, const int32_t *bt, const int32_t *bi, int S,
-                                     int K, int D) {
-  return pack_blob(ft, fi, nullptr, bt, bi, nullptr, nullptr, nullptr, nullptr, S, K, D, nullptr, 0);
-}
-
-int chain_b200_den_prepare(const int32_t *ft, const int32_t *fi, const float *fp, const int32_t *bt,
-                           const int32_t *bi, const float *bp, const float *leaky, const float *init,
-                           const float *fin, int S, int K, int D, void *blob, int64_t blob_bytes) {
-  if (!blob) return CHAIN_B200_ERR_INVALID_ARG;
-  const int64_t r = pack_blob(ft, fi, fp, bt, bi, bp, leaky, init, fin, S, K, D, blob, blob_bytes);
-  return r < 0 ? (int)r : CHAIN_B200_OK;
-}
 
 size_t chain_b200_den_workspace_bytes(const void *blob_host, int B, int T) {
   const BlobHeader *h = (const BlobHeader *)blob_host;
@@ -754,11 +590,15 @@ int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev,
 
   DenParams p;
   for (int i = 0; i < 3; i++) {
-    p.view[i].rows = (const int32_t *)(bd + h.view[i].off_rows);
-    p.view[i].desc = (const int2 *)(bd + h.view[i].off_desc);
-    p.view[i].warp_ptr = (const int32_t *)(bd + h.view[i].off_warp_ptr);
-    p.view[i].warp_slices = (const int32_t *)(bd + h.view[i].off_warp_slices);
-    p.view[i].recs = (const uint2 *)(bd + h.view[i].off_recs);
+    const BlobView &bv = h.view[i];
+    p.view[i].rows = (const int32_t *)(bd + bv.off_rows);
+    p.view[i].width = (const int32_t *)(bd + bv.off_width);
+    p.view[i].warp_ptr = (const int32_t *)(bd + bv.off_warp_ptr);
+    p.view[i].warp_slices = (const int32_t *)(bd + bv.off_warp_slices);
+    p.view[i].warp_stream = (const int64_t *)(bd + bv.off_warp_stream);
+    p.view[i].recs = (const uint2 *)(bd + bv.off_recs);
+    p.view[i].split = (const int32_t *)(bd + bv.off_split);
+    p.view[i].n_split = bv.n_split;
   }
   p.leaky = (const float *)(bd + h.off_leaky);
   p.init = (const float *)(bd + h.off_init);
