@@ -4,6 +4,8 @@
 // /root/reference/openfst_binding/src/fstext.cc:19-117 or by pychain_b200.graph.Fst).
 // Output: the blob consumed by den_shared.cu.  Pure host C++ (no CUDA calls).
 #include <algorithm>
+#include <array>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -53,20 +55,165 @@ static int quarter_wavefronts(const uint32_t *idx, int n) {
   return worst;
 }
 
-// Order the arcs of the 32 units of a slice into columns.  `cols[k][lane]` = index into
-// units[lane].arcs or -1 (idle).  Baseline: the units' own arc order.
-static void arrange_slice(const std::vector<const Unit *> &lanes, int width, std::vector<int> &cols) {
+// ---- deterministic RNG for the packer's local search -------------------------------------
+struct Rng {
+  uint64_t s;
+  explicit Rng(uint64_t seed) : s(seed * 0x9E3779B97F4A7C15ull + 0x1234567ull) {}
+  uint32_t next() {
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    return (uint32_t)(s >> 32);
+  }
+  uint32_t below(uint32_t n) { return (uint32_t)(((uint64_t)next() * n) >> 32); }
+  double unit() { return next() * (1.0 / 4294967296.0); }
+};
+
+static int pack_effort() {
+  const char *e = getenv("CHAIN_B200_PACK_EFFORT");
+  return e ? std::max(0, atoi(e)) : 2;
+}
+
+// A. Regroup the (length-sorted) units so that every run of 8 consecutive units -- the rows a
+// quarter-warp processes side by side -- has flat histograms of bank groups (index mod 8) for
+// both gathered operands.  Flat histograms are what makes a conflict-free column order exist.
+static void balance_quarters(const std::vector<Unit> &units, std::vector<int> &order) {
+  const int n = (int)order.size();
+  std::vector<std::array<uint16_t, 16>> hist(units.size());
+  for (size_t u = 0; u < units.size(); u++) {
+    hist[u].fill(0);
+    for (const Arc &a : units[u].arcs) { hist[u][a.ab & 7u]++; hist[u][8 + ((a.ab >> 16) & 7u)]++; }
+  }
+  std::vector<int> out;
+  out.reserve(n);
+  std::vector<char> used(n, 0);
+  int head = 0;
+  const int WIN = 160;
+  while ((int)out.size() < n) {
+    while (head < n && used[head]) head++;
+    const int first = order[head];
+    used[head] = 1;
+    out.push_back(first);
+    long sum[16];
+    for (int c = 0; c < 16; c++) sum[c] = hist[first][c];
+    const size_t len0 = units[first].arcs.size();
+    for (int pick = 1; pick < 8 && (int)out.size() < n; pick++) {
+      int best = -1;
+      long best_cost = 0;
+      int seen = 0;
+      for (int j = head + 1; j < n && seen < WIN; j++) {
+        if (used[j]) continue;
+        const int u = order[j];
+        // keep slices tight: prefer equal length; allow one shorter once the equal ones run out
+        if (units[u].arcs.size() + 1 < len0 && seen >= 8) break;
+        seen++;
+        long cost = 0;
+        for (int c = 0; c < 16; c++) { const long t = sum[c] + hist[u][c]; cost += t * t; }
+        cost = cost * 4 + (long)(len0 - units[u].arcs.size()) * 64;
+        if (best < 0 || cost < best_cost) { best = j; best_cost = cost; }
+      }
+      if (best < 0) break;
+      used[best] = 1;
+      out.push_back(order[best]);
+      for (int c = 0; c < 16; c++) sum[c] += hist[order[best]][c];
+    }
+  }
+  order.swap(out);
+}
+
+// B. Column order inside one quarter (8 lanes x W columns): simulated annealing over swaps of
+// two entries of one lane, minimising the modelled wavefronts sum_k (max multiplicity of the
+// a-bank-groups + max multiplicity of the b-bank-groups), ties broken towards flat counts.
+static void anneal_quarter(const Unit *const *lanes, int W, int *arr /* [8][W] arc index or -1 */, Rng &rng,
+                           int effort) {
+  std::vector<uint8_t> c1((size_t)W * 8, 0), c2((size_t)W * 8, 0);
+  auto col_of = [&](int i, int k, int &x, int &y) {
+    const int j = arr[i * W + k];
+    if (j < 0) { x = y = -1; return; }
+    const uint32_t ab = lanes[i]->arcs[j].ab;
+    x = ab & 7u; y = (ab >> 16) & 7u;
+  };
+  for (int i = 0; i < 8; i++)
+    for (int k = 0; k < W; k++) {
+      int x, y;
+      col_of(i, k, x, y);
+      if (x >= 0) { c1[k * 8 + x]++; c2[k * 8 + y]++; }
+    }
+  auto col_cost = [&](int k) {
+    int m1 = 0, m2 = 0, sq = 0;
+    for (int c = 0; c < 8; c++) {
+      const int u = c1[k * 8 + c], v = c2[k * 8 + c];
+      m1 = std::max(m1, u); m2 = std::max(m2, v);
+      sq += u * u + v * v;
+    }
+    return 24 * (m1 + m2) + sq;
+  };
+  std::vector<int> cc(W);
+  long total = 0;
+  for (int k = 0; k < W; k++) { cc[k] = col_cost(k); total += cc[k]; }
+  std::vector<int> best(arr, arr + 8 * W);
+  long best_total = total;
+  const int moves = effort * 220 * W + 400;
+  double T = 10.0;
+  const double decay = pow(0.05 / T, 1.0 / moves);
+  for (int it = 0; it < moves; it++, T *= decay) {
+    const int i = rng.below(8), k1 = rng.below(W);
+    int k2 = rng.below(W - 1);
+    if (k2 >= k1) k2++;
+    const int j1 = arr[i * W + k1], j2 = arr[i * W + k2];
+    if (j1 < 0 && j2 < 0) continue;
+    int x1, y1, x2, y2;
+    col_of(i, k1, x1, y1);
+    col_of(i, k2, x2, y2);
+    auto mv = [&](int k, int x, int y, int d) {
+      if (x >= 0) { c1[k * 8 + x] += d; c2[k * 8 + y] += d; }
+    };
+    mv(k1, x1, y1, -1); mv(k2, x2, y2, -1); mv(k1, x2, y2, +1); mv(k2, x1, y1, +1);
+    const int n1 = col_cost(k1), n2 = col_cost(k2);
+    const int delta = n1 + n2 - cc[k1] - cc[k2];
+    if (delta <= 0 || rng.unit() < exp(-delta / T)) {
+      arr[i * W + k1] = j2; arr[i * W + k2] = j1;
+      cc[k1] = n1; cc[k2] = n2;
+      total += delta;
+      if (total < best_total) { best_total = total; std::copy(arr, arr + 8 * W, best.begin()); }
+    } else {
+      mv(k1, x2, y2, -1); mv(k2, x1, y1, -1); mv(k1, x1, y1, +1); mv(k2, x2, y2, +1);
+    }
+  }
+  std::copy(best.begin(), best.end(), arr);
+}
+
+// Order the arcs of the 32 units of a slice into columns.  `cols[k*32+lane]` = index into
+// lanes[lane]->arcs or -1 (idle).
+static void arrange_slice(const std::vector<const Unit *> &lanes, int width, std::vector<int> &cols, Rng &rng,
+                          int effort) {
   cols.assign((size_t)width * 32, -1);
   for (int l = 0; l < 32; l++) {
     if (!lanes[l]) continue;
     const int n = (int)lanes[l]->arcs.size();
     for (int k = 0; k < n; k++) cols[(size_t)k * 32 + l] = k;
   }
+  if (effort <= 0 || width < 2) return;
+  static const Unit empty_unit{-1, {}};
+  std::vector<int> arr((size_t)8 * width);
+  for (int q = 0; q < 4; q++) {
+    const Unit *ql[8];
+    bool any = false;
+    for (int i = 0; i < 8; i++) {
+      ql[i] = lanes[q * 8 + i] ? lanes[q * 8 + i] : &empty_unit;
+      any |= !ql[i]->arcs.empty();
+      for (int k = 0; k < width; k++) arr[(size_t)i * width + k] = cols[(size_t)k * 32 + q * 8 + i];
+    }
+    if (!any) continue;
+    anneal_quarter(ql, width, arr.data(), rng, effort);
+    for (int i = 0; i < 8; i++)
+      for (int k = 0; k < width; k++) cols[(size_t)k * 32 + q * 8 + i] = arr[(size_t)i * width + k];
+  }
 }
 
 static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, const std::vector<uint32_t> &ab,
-                       const float *w, int n_a, int n_b, ViewBuild &v) {
+                       const float *w, int n_a, int n_b, bool structure_only, ViewBuild &v) {
   v.n_rows = n_rows;
+  const int effort = pack_effort();
+  Rng rng(0xC0FFEEull + (uint64_t)n_rows * 7919u + (uint64_t)K);
   // rows -> arc lists, arc order inside a row = CSR order (the reference's summation order)
   std::vector<int32_t> deg(n_rows, 0);
   for (int k = 0; k < K; k++) deg[row_of[k]]++;
@@ -108,6 +255,7 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(),
                    [&](int x, int y) { return units[x].arcs.size() > units[y].arcs.size(); });
+  if (effort >= 1) balance_quarters(units, order);
   const int n_slices = ((int)units.size() + 31) / 32;
   v.n_slices = n_slices;
   v.rows.assign((size_t)n_slices * 32, -1);
@@ -127,7 +275,7 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
     }
     width += width & 1;
     std::vector<int> cols;
-    arrange_slice(lanes, width, cols);
+    arrange_slice(lanes, width, cols, rng, structure_only ? 0 : effort);
     width = (int)(cols.size() / 32);
     v.width[s] = width;
     s_ab[s].assign((size_t)width * 32, 0u);
@@ -141,9 +289,8 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
         if (j >= 0) {
           rec = lanes[l]->arcs[j].ab;
           wt = lanes[l]->arcs[j].w;
-        } else {  // idle lane: weight 0; index = the lane's own bank group so idle lanes never collide
-          const uint32_t q = (uint32_t)(l & 7);
-          rec = (q < na ? q : 0u) | ((q < nb ? q : 0u) << 16);
+        } else {  // idle lane: weight 0, placed below
+          rec = 0xffffffffu;
         }
         s_ab[s][(size_t)k * 32 + l] = rec;
         s_w[s][(size_t)k * 32 + l] = wt;
@@ -151,6 +298,22 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
         ib[l] = rec >> 16;
       }
       for (int q = 0; q < 4; q++) {
+        // idle lanes read element `g` of a bank group g nobody else uses in this quarter-column
+        unsigned used_a = 0, used_b = 0;
+        for (int i = 0; i < 8; i++)
+          if (s_ab[s][(size_t)k * 32 + q * 8 + i] != 0xffffffffu) { used_a |= 1u << (ia[q * 8 + i] & 7u); used_b |= 1u << (ib[q * 8 + i] & 7u); }
+        for (int i = 0; i < 8; i++) {
+          const size_t pos = (size_t)k * 32 + q * 8 + i;
+          if (s_ab[s][pos] != 0xffffffffu) continue;
+          uint32_t ga = 0, gb = 0;
+          while (ga < 7 && ((used_a >> ga) & 1u)) ga++;
+          while (gb < 7 && ((used_b >> gb) & 1u)) gb++;
+          used_a |= 1u << ga; used_b |= 1u << gb;
+          if (ga >= na) ga = 0;
+          if (gb >= nb) gb = 0;
+          s_ab[s][pos] = ga | (gb << 16);
+          ia[q * 8 + i] = ga; ib[q * 8 + i] = gb;
+        }
         v.predicted += quarter_wavefronts(ia + 8 * q, 8) + quarter_wavefronts(ib + 8 * q, 8);
         v.ideal += 2;
       }
@@ -220,9 +383,10 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
     row_pdf[k] = fn; ab_gam[k] = (uint32_t)fs | ((uint32_t)fd << 16);  // forward-CSR order
   }
   ViewBuild vb[3];
-  build_view(S, Kv, row_dst, ab_fwd, bp, S, D, vb[0]);
-  build_view(S, Kv, row_src, ab_bwd, fp, S, D, vb[1]);
-  build_view(D, Kv, row_pdf, ab_gam, fp, S, S, vb[2]);
+  const bool so = (out == nullptr);
+  build_view(S, Kv, row_dst, ab_fwd, bp, S, D, so, vb[0]);
+  build_view(S, Kv, row_src, ab_bwd, fp, S, D, so, vb[1]);
+  build_view(D, Kv, row_pdf, ab_gam, fp, S, S, so, vb[2]);
 
   BlobHeader h;
   memset(&h, 0, sizeof(h));
