@@ -111,7 +111,10 @@ int chain_b200_forward_backward_log_domain(
  * chain_b200_den_workspace_bytes: device workspace for a batch of B x T.
  * chain_b200_den_forward_backward: same outputs as chain_b200_forward_backward;
  *   needs both the host copy of the blob (read for launch geometry only) and
- *   the device copy. */
+ *   the device copy.  `blob_dev` may hold `blob_copies` >= 1 identical copies of
+ *   the blob back to back (stride = the blob's byte size, which is a multiple of
+ *   256): every CTA streams the same records every frame, and spreading the CTAs
+ *   over several copies (8 is a good number) avoids L2 hot-spotting. */
 int64_t chain_b200_den_prepare_bytes(
     const int32_t *fwd_trans_host, const int32_t *fwd_idx_host,
     const int32_t *bwd_trans_host, const int32_t *bwd_idx_host,
@@ -126,7 +129,7 @@ int chain_b200_den_prepare(
 size_t chain_b200_den_workspace_bytes(const void *blob_host, int B, int T);
 
 int chain_b200_den_forward_backward(
-    const void *blob_host, const void *blob_dev,
+    const void *blob_host, const void *blob_dev, int blob_copies,
     const float *x_dev, const int64_t *lengths_dev,
     int B, int T, int D, float leaky_coeff, unsigned flags,
     float *objf_dev, float *logp_dev, float *grad_dev, int32_t *ok_dev, float *diag_dev,

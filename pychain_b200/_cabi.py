@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libchain_b200.so")
+LIB_PATH = os.environ.get("CHAIN_B200_LIB") or os.path.join(_PKG, "lib", "libchain_b200.so")
 
 c_int, c_uint, c_float, c_size_t, c_void_p, c_int64 = (
     ctypes.c_int, ctypes.c_uint, ctypes.c_float, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int64)
@@ -30,7 +30,8 @@ SIGNATURES = {
     "chain_b200_den_prepare": (c_int, [c_void_p] * 9 + [c_int] * 3 + [c_void_p, c_int64]),
     "chain_b200_den_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "chain_b200_den_forward_backward": (
-        c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_uint] + [c_void_p] * 5 + [c_void_p, c_size_t, c_int, c_void_p]),
+        c_int, [c_void_p] * 2 + [c_int] + [c_void_p] * 2 + [c_int] * 3 + [c_float, c_uint] + [c_void_p] * 5 +
+        [c_void_p, c_size_t, c_int, c_void_p]),
 }
 
 _lib = None

@@ -10,9 +10,13 @@
 //
 // 32 rows form a slice (one row per lane); slices are dealt to the DEN_NW warps of a CTA and
 // each warp's records are stored as ONE contiguous stream in processing order
-// ([slice][k][lane], 8 bytes each: {a:16 | b:16, weight:f32}) followed by kFifoPairs*2
-// null iterations, so the kernel can run a register FIFO of record loads ahead of use
-// without bounds checks.  Slice widths are even (records are consumed in pairs).
+// ([slice][k][lane], 8 bytes each: {a:16 | b:16, weight:f32}).  Records are consumed in
+// pairs; the SIGN BIT of the weight of the second record of a pair marks "last pair of this
+// slice" (weights are probabilities, >= 0), so the kernel's inner loop is one flat counted
+// loop over pairs with a register FIFO of kFifoPairs pairs of loads in flight -- no per-slice
+// control flow, no bounds checks (each stream is padded to a multiple of kFifoPairs pairs
+// plus kFifoPairs run-out pairs).  The row each lane owns in each slice comes from a
+// parallel per-warp stream of row codes, read one slice ahead.
 // Rows whose degree exceeds the view's cap are split into sub-rows; a sub-row writes its
 // partial sum to a scratch slot and the listed owner adds the slots up in order.
 #pragma once
@@ -21,19 +25,20 @@
 namespace chainb200 {
 
 constexpr uint32_t kBlobMagic = 0x42324348u;  // "HC2B"
-constexpr uint32_t kBlobVersion = 3;
+constexpr uint32_t kBlobVersion = 6;
 constexpr int DEN_NW = 16;           // warps per CTA the slice schedule is built for
 constexpr int DEN_NT = DEN_NW * 32;
-constexpr int kFifoPairs = 3;        // record pairs in flight per lane
+#ifndef CHAIN_B200_FIFO_PAIRS
+#define CHAIN_B200_FIFO_PAIRS 4
+#endif
+constexpr int kFifoPairs = CHAIN_B200_FIFO_PAIRS;  // record pairs in flight per lane
 
 struct BlobView {
   int32_t n_rows, n_slices, n_split, n_sub;
   int64_t n_recs;
-  int64_t off_rows;         // int32 [n_slices*32]  >= 0 row id; -1 idle lane; <= -2: sub-row slot (-2 - slot)
-  int64_t off_width;        // int32 [n_slices]     even
-  int64_t off_warp_ptr;     // int32 [DEN_NW+1]     range in warp_slices
-  int64_t off_warp_slices;  // int32 [n_slices]     slice ids in each warp's processing order
-  int64_t off_warp_stream;  // int64 [DEN_NW]       record offset of each warp's stream
+  int64_t off_warp_info;    // int64 [DEN_NW][3]    {record offset of the stream, pairs to run (multiple of kFifoPairs), row-code offset}
+  int64_t off_rows;         // int32 [(n_slices + 3*DEN_NW)*32]  per warp, per slice in processing order, + one idle slice:
+                            //                      >= 0 row id; -1 idle lane; <= -2: sub-row slot (-2 - slot)
   int64_t off_recs;         // uint2 [n_recs]
   int64_t off_split;        // int32 [n_split*3]    {row, first slot, slot count}
 };

@@ -29,8 +29,8 @@ struct Unit {            // a row, or one piece of a split row
 
 struct ViewBuild {
   int n_rows = 0, n_slices = 0, n_split = 0, n_sub = 0;
-  std::vector<int32_t> rows, width, warp_ptr, warp_slices, split;
-  std::vector<int64_t> warp_stream;
+  std::vector<int32_t> rows, width, split;  // rows: per slice while building, re-emitted per warp below
+  std::vector<int64_t> warp_info;            // [DEN_NW][3]
   std::vector<uint32_t> rec_ab;
   std::vector<float> rec_w;
   double predicted = 0, ideal = 0;
@@ -273,7 +273,7 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
       v.rows[i] = lanes[l]->row_code;
       width = std::max(width, (int)lanes[l]->arcs.size());
     }
-    width += width & 1;
+    width = std::max(2, width + (width & 1));  // pairs; an empty slice still runs its epilogue
     std::vector<int> cols;
     arrange_slice(lanes, width, cols, rng, structure_only ? 0 : effort);
     width = (int)(cols.size() / 32);
@@ -330,22 +330,33 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
     per[best].push_back(s);
     load[best] += v.width[s] + 4;
   }
-  v.warp_ptr.assign(DEN_NW + 1, 0);
-  v.warp_slices.clear();
-  v.warp_stream.assign(DEN_NW, 0);
+  v.warp_info.assign((size_t)DEN_NW * 3, 0);
   v.rec_ab.clear();
   v.rec_w.clear();
+  std::vector<int32_t> rows_seq;
+  rows_seq.reserve(((size_t)n_slices + 3 * DEN_NW) * 32);
   for (int wv = 0; wv < DEN_NW; wv++) {
-    v.warp_ptr[wv + 1] = v.warp_ptr[wv] + (int32_t)per[wv].size();
-    v.warp_stream[wv] = (int64_t)v.rec_ab.size();
+    const size_t rec0 = v.rec_ab.size();
+    v.warp_info[3 * wv + 0] = (int64_t)rec0;
+    v.warp_info[3 * wv + 2] = (int64_t)rows_seq.size();
     for (int s : per[wv]) {
-      v.warp_slices.push_back(s);
+      rows_seq.insert(rows_seq.end(), v.rows.begin() + (size_t)s * 32, v.rows.begin() + (size_t)s * 32 + 32);
       v.rec_ab.insert(v.rec_ab.end(), s_ab[s].begin(), s_ab[s].end());
       v.rec_w.insert(v.rec_w.end(), s_w[s].begin(), s_w[s].end());
+      // end-of-slice flag: sign bit of the weight of the last record of every lane
+      const size_t last = v.rec_w.size() - 32;
+      for (int l = 0; l < 32; l++) v.rec_w[last + l] = -fabsf(v.rec_w[last + l]) - 0.0f;
+      for (int l = 0; l < 32; l++)
+        if (!std::signbit(v.rec_w[last + l])) v.rec_w[last + l] = -0.0f;
     }
-    v.rec_ab.insert(v.rec_ab.end(), (size_t)kFifoPairs * 2 * 32, 0u);  // FIFO run-out
-    v.rec_w.insert(v.rec_w.end(), (size_t)kFifoPairs * 2 * 32, 0.f);
+    rows_seq.insert(rows_seq.end(), 3 * 32, -1);  // the row prefetch runs slices ahead
+    size_t pairs = (v.rec_ab.size() - rec0) / 64;
+    const size_t run = (pairs + 2 * kFifoPairs - 1) / (2 * kFifoPairs) * (2 * kFifoPairs);
+    v.warp_info[3 * wv + 1] = (int64_t)run;
+    v.rec_ab.insert(v.rec_ab.end(), (run - pairs + kFifoPairs) * 64, 0u);  // idle pairs + FIFO run-out
+    v.rec_w.insert(v.rec_w.end(), (run - pairs + kFifoPairs) * 64, 0.f);
   }
+  v.rows.swap(rows_seq);
 }
 
 }  // namespace
@@ -371,6 +382,9 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
     for (int k = fi[2 * s]; k < fi[2 * s + 1]; k++)
       if (ft[3 * k] != s) return CHAIN_B200_ERR_INVALID_ARG;
   }
+  if (fp && bp)
+    for (int k = 0; k < Kv; k++)
+      if (!(fp[k] >= 0.f) || !(bp[k] >= 0.f)) return CHAIN_B200_ERR_INVALID_ARG;  // probabilities (sign bit is a flag)
   std::vector<int32_t> row_dst(Kv), row_src(Kv), row_pdf(Kv);
   std::vector<uint32_t> ab_fwd(Kv), ab_bwd(Kv), ab_gam(Kv);
   for (int k = 0; k < Kv; k++) {
@@ -402,11 +416,8 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
     h.max_sub = std::max(h.max_sub, b.n_sub);
     h.predicted_wavefronts[i] = b.predicted;
     h.ideal_wavefronts[i] = b.ideal;
+    bv.off_warp_info = (int64_t)off; off = align_up(off + b.warp_info.size() * 8);
     bv.off_rows = (int64_t)off; off = align_up(off + b.rows.size() * 4);
-    bv.off_width = (int64_t)off; off = align_up(off + b.width.size() * 4);
-    bv.off_warp_ptr = (int64_t)off; off = align_up(off + b.warp_ptr.size() * 4);
-    bv.off_warp_slices = (int64_t)off; off = align_up(off + b.warp_slices.size() * 4 + 4);
-    bv.off_warp_stream = (int64_t)off; off = align_up(off + b.warp_stream.size() * 8);
     bv.off_recs = (int64_t)off; off = align_up(off + b.rec_ab.size() * 8 + 8);
     bv.off_split = (int64_t)off; off = align_up(off + b.split.size() * 4 + 4);
   }
@@ -422,11 +433,8 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
   for (int i = 0; i < 3; i++) {
     const BlobView &bv = h.view[i];
     const ViewBuild &b = vb[i];
+    memcpy(base + bv.off_warp_info, b.warp_info.data(), b.warp_info.size() * 8);
     memcpy(base + bv.off_rows, b.rows.data(), b.rows.size() * 4);
-    memcpy(base + bv.off_width, b.width.data(), b.width.size() * 4);
-    memcpy(base + bv.off_warp_ptr, b.warp_ptr.data(), b.warp_ptr.size() * 4);
-    memcpy(base + bv.off_warp_slices, b.warp_slices.data(), b.warp_slices.size() * 4);
-    memcpy(base + bv.off_warp_stream, b.warp_stream.data(), b.warp_stream.size() * 8);
     memcpy(base + bv.off_split, b.split.data(), b.split.size() * 4);
     uint32_t *rec = (uint32_t *)(base + bv.off_recs);
     for (size_t j = 0; j < b.rec_ab.size(); j++) {

@@ -34,8 +34,8 @@ namespace chainb200 {
 
 // ------------------------------------------------------------------------------- device
 struct DView {
-  const int32_t *rows, *width, *warp_ptr, *warp_slices, *split;
-  const int64_t *warp_stream;
+  const int64_t *warp_info;  // [DEN_NW][3] {stream offset, pairs to run, row-code offset}
+  const int32_t *rows, *split;
   const uint2 *recs;
   int n_split;
 };
@@ -51,6 +51,8 @@ struct DenParams {
   float *logp, *grad, *diag;
   float *alpha_ws, *tot_ws;
   int num_groups, use_tma_x;
+  int n_rep;           // copies of the blob laid out back to back on the device
+  size_t rep_stride;   // bytes between copies
 };
 
 template <int G> struct Vec;
@@ -83,6 +85,15 @@ __device__ __forceinline__ uint2 ldg_stream(const uint2 *p) {
   asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
 }
+// Refill a FIFO slot IN PLACE: the "+r" operands make the load depend on the slot's previous
+// contents, so the compiler can neither hoist it above the consumers of the old pair nor
+// stage it through a temporary (a copy out of a temporary would wait for the load).
+__device__ __forceinline__ void ldg_stream_into(uint2 &r, const uint2 *p) {
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "+r"(r.x), "+r"(r.y) : "l"(p));
+}
+__device__ __forceinline__ void ldg_into(int &r, const int32_t *p) {
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "+r"(r) : "l"(p));
+}
 
 // ---- mbarrier / TMA bulk helpers (cp.async.bulk: SASS UBLKCP) ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,51 +122,72 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int G>
-__device__ __forceinline__ void consume_rec(const uint2 r, const float *__restrict__ A, const float *__restrict__ Bv,
-                                            float (&acc)[G]) {
+__device__ __forceinline__ void consume_rec(const uint32_t ab, const float w, const float *__restrict__ A,
+                                            const float *__restrict__ Bv, float (&acc)[G]) {
   float a[G], b[G];
-  ld_vec<G>(A + (r.x & 0xffffu) * G, a);
-  ld_vec<G>(Bv + (r.x >> 16) * G, b);
-  const float w = __uint_as_float(r.y);
+  ld_vec<G>(A + (ab & 0xffffu) * G, a);
+  ld_vec<G>(Bv + (ab >> 16) * G, b);
 #pragma unroll
   for (int g = 0; g < G; g++) acc[g] = fmaf(a[g] * w, b[g], acc[g]);
 }
 
 // One SELL pass: every lane owns one row (or sub-row) of each of its warp's slices and
 // accumulates sum_k w_k * A[a_k][g] * Bv[b_k][g] over the row's records.  The warp's
-// records are one contiguous stream; a register FIFO keeps kFifoPairs pairs of record
-// loads (L2 latency) in flight ahead of their use, across slice boundaries.
+// records are one contiguous stream consumed in pairs by a flat counted loop.  Two register
+// banks of kFifoPairs pairs alternate: while one bank is consumed the other is being filled
+// (its previous contents are dead), so kFifoPairs pairs of record loads are always in
+// flight to cover the L2 latency and no load ever lands in a register that is still live.
+// The sign bit of the second weight of a pair ends a slice: run the epilogue for the lane's
+// row and move to the next row code (fetched two slices ahead).
 template <int G, class Epi>
 __device__ __forceinline__ void sell_pass(const DView &v, const float *__restrict__ A, const float *__restrict__ Bv,
                                           float *__restrict__ partial, int warp, int lane, Epi &epi) {
-  const uint2 *sp = v.recs + v.warp_stream[warp] + lane;
-  uint2 f[kFifoPairs][2];
+  const uint2 *sp = v.recs + v.warp_info[3 * warp] + lane;
+  const int npairs = (int)v.warp_info[3 * warp + 1];
+  const int32_t *rp = v.rows + v.warp_info[3 * warp + 2] + lane;
+  uint2 fa[kFifoPairs][2], fb[kFifoPairs][2];
 #pragma unroll
   for (int d = 0; d < kFifoPairs; d++) {
-    f[d][0] = ldg_stream(sp + (2 * d) * 32);
-    f[d][1] = ldg_stream(sp + (2 * d + 1) * 32);
+    fa[d][0] = ldg_stream(sp + (2 * d) * 32);
+    fa[d][1] = ldg_stream(sp + (2 * d + 1) * 32);
   }
   sp += 2 * kFifoPairs * 32;
-  const int s1 = v.warp_ptr[warp + 1];
-  for (int si = v.warp_ptr[warp]; si < s1; si++) {
-    const int slice = v.warp_slices[si];
-    const int w = __ldg(&v.width[slice]);
-    const int row = __ldg(&v.rows[slice * 32 + lane]);
-    float acc[G];
+  int row = __ldg(rp), row_n1 = __ldg(rp + 32), row_n2 = __ldg(rp + 64);
+  rp += 96;
+  float acc[G];
 #pragma unroll
-    for (int g = 0; g < G; g++) acc[g] = 0.f;
-    for (int k = 0; k < w; k += 2) {
-      const uint2 r0 = f[0][0], r1 = f[0][1];
+  for (int g = 0; g < G; g++) acc[g] = 0.f;
+  auto process = [&](const uint2 r0, const uint2 r1) {
+    consume_rec<G>(r0.x, __uint_as_float(r0.y), A, Bv, acc);
+    consume_rec<G>(r1.x, __uint_as_float(r1.y & 0x7fffffffu), A, Bv, acc);
+    if (r1.y & 0x80000000u) {  // warp-uniform: last pair of the slice
+      if (row >= 0) epi(row, acc);
+      else if (row <= -2) st_vec<G>(partial + (size_t)(-2 - row) * G, acc);
 #pragma unroll
-      for (int d = 0; d + 1 < kFifoPairs; d++) { f[d][0] = f[d + 1][0]; f[d][1] = f[d + 1][1]; }
-      f[kFifoPairs - 1][0] = ldg_stream(sp);
-      f[kFifoPairs - 1][1] = ldg_stream(sp + 32);
-      sp += 64;
-      consume_rec<G>(r0, A, Bv, acc);
-      consume_rec<G>(r1, A, Bv, acc);
+      for (int g = 0; g < G; g++) acc[g] = 0.f;
+      row = row_n1;
+      row_n1 = row_n2;
+      row_n2 = __ldg(rp);
+      rp += 32;
     }
-    if (row >= 0) epi(row, acc);
-    else if (row <= -2) st_vec<G>(partial + (size_t)(-2 - row) * G, acc);
+  };
+  for (int j = 0; j < npairs; j += 2 * kFifoPairs) {
+#pragma unroll
+    for (int d = 0; d < kFifoPairs; d++) {
+      fb[d][0] = ldg_stream(sp + (2 * d) * 32);
+      fb[d][1] = ldg_stream(sp + (2 * d + 1) * 32);
+    }
+    sp += 2 * kFifoPairs * 32;
+#pragma unroll
+    for (int d = 0; d < kFifoPairs; d++) process(fa[d][0], fa[d][1]);
+#pragma unroll
+    for (int d = 0; d < kFifoPairs; d++) {
+      fa[d][0] = ldg_stream(sp + (2 * d) * 32);
+      fa[d][1] = ldg_stream(sp + (2 * d + 1) * 32);
+    }
+    sp += 2 * kFifoPairs * 32;
+#pragma unroll
+    for (int d = 0; d < kFifoPairs; d++) process(fb[d][0], fb[d][1]);
   }
 }
 
@@ -218,6 +250,18 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
   const bool clamp_x = (p.flags & CHAIN_B200_CLAMP_X) && !(p.flags & CHAIN_B200_X_IS_EXP);
   const bool exp_x = !(p.flags & CHAIN_B200_X_IS_EXP);
 
+  // every CTA streams the same packed records every frame; spreading the CTAs over n_rep
+  // identical copies keeps them from queueing on the same L2 lines at the same time
+  DView views[3];
+  {
+    const size_t rep_off = (size_t)(blockIdx.x % p.n_rep) * p.rep_stride;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      views[i] = p.view[i];
+      views[i].recs = reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(p.view[i].recs) + rep_off);
+      views[i].rows = reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(p.view[i].rows) + rep_off);
+    }
+  }
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
@@ -338,7 +382,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         for (int g = 0; g < G; g++) { o[g] = acc[g] * inv[g]; part[g] += o[g]; }
         st_vec<G>(Bn + (size_t)row * G, o);
       };
-      sell_pass<G>(p.view[0], A, x_s, partial, warp, lane, epi_fwd);
+      sell_pass<G>(views[0], A, x_s, partial, warp, lane, epi_fwd);
       if (p.view[0].n_split) { __syncthreads(); fixup_split<G>(p.view[0], partial, epi_fwd); }
 #pragma unroll
       for (int g = 0; g < G; g++) {
@@ -437,7 +481,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         for (int g = 0; g < G; g++) { o[g] = acc[g] * xv[g] * inv[g]; gsum[g] += o[g]; }
         st_vec<G>(gam_s + (size_t)row * G, o);
       };
-      sell_pass<G>(p.view[2], P, Q, partial, warp, lane, epi_gam);
+      sell_pass<G>(views[2], P, Q, partial, warp, lane, epi_gam);
       if (p.view[2].n_split) { __syncthreads(); fixup_split<G>(p.view[2], partial, epi_gam); }
       __syncthreads();  // gamma rows complete; everybody done reading P
 
@@ -458,7 +502,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         for (int g = 0; g < G; g++) { o[g] = acc[g] * inv[g]; lpart[g] = fmaf(o[g], l, lpart[g]); }
         st_vec<G>(P + (size_t)row * G, o);
       };
-      sell_pass<G>(p.view[1], Q, x_s, partial, warp, lane, epi_bwd);
+      sell_pass<G>(views[1], Q, x_s, partial, warp, lane, epi_bwd);
       if (p.view[1].n_split) { __syncthreads(); fixup_split<G>(p.view[1], partial, epi_bwd); }
 #pragma unroll
       for (int g = 0; g < G; g++) {
@@ -563,7 +607,7 @@ size_t chain_b200_den_workspace_bytes(const void *blob_host, int B, int T) {
   return den_ws_layout(*h, B, T).total;
 }
 
-int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev, const float *x,
+int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev, int blob_copies, const float *x,
                                     const int64_t *lengths, int B, int T, int D, float coeff, unsigned flags,
                                     float *objf, float *logp, float *grad, int32_t *ok, float *diag, void *ws,
                                     size_t ws_bytes, int device, void *stream_v) {
@@ -591,11 +635,8 @@ int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev,
   DenParams p;
   for (int i = 0; i < 3; i++) {
     const BlobView &bv = h.view[i];
+    p.view[i].warp_info = (const int64_t *)(bd + bv.off_warp_info);
     p.view[i].rows = (const int32_t *)(bd + bv.off_rows);
-    p.view[i].width = (const int32_t *)(bd + bv.off_width);
-    p.view[i].warp_ptr = (const int32_t *)(bd + bv.off_warp_ptr);
-    p.view[i].warp_slices = (const int32_t *)(bd + bv.off_warp_slices);
-    p.view[i].warp_stream = (const int64_t *)(bd + bv.off_warp_stream);
     p.view[i].recs = (const uint2 *)(bd + bv.off_recs);
     p.view[i].split = (const int32_t *)(bd + bv.off_split);
     p.view[i].n_split = bv.n_split;
@@ -613,6 +654,8 @@ int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev,
   p.tot_ws = (float *)(base + w.tot);
   p.num_groups = (B + G - 1) / G;
   p.use_tma_x = (D % 4 == 0) && (((uintptr_t)x & 15u) == 0);
+  p.n_rep = blob_copies > 0 ? blob_copies : 1;
+  p.rep_stride = (size_t)h.total_bytes;
 
   const int grid = std::min(p.num_groups, num_sms);
   cudaError_t e;

@@ -7,6 +7,7 @@ a CPU `x` raises.
 from __future__ import annotations
 
 import ctypes
+import os
 from collections import OrderedDict
 
 import torch
@@ -143,8 +144,8 @@ class PreparedDenGraph(object):
     """A denominator graph packed once by chain_b200_den_prepare: host blob
     (launch geometry) + its device copy."""
 
-    def __init__(self, blob_host, blob_dev, S, K, D):
-        self.blob_host, self.blob_dev, self.S, self.K, self.D = blob_host, blob_dev, S, K, D
+    def __init__(self, blob_host, blob_dev, copies, S, K, D):
+        self.blob_host, self.blob_dev, self.copies, self.S, self.K, self.D = blob_host, blob_dev, copies, S, K, D
 
 
 _prepared_cache = OrderedDict()
@@ -171,8 +172,9 @@ def prepare_den_graph(graph_tensors, num_states, D, device):
         torch.empty(int(nbytes), dtype=torch.uint8)
     st = lib.chain_b200_den_prepare(*[_ptr(t) for t in host], S, K, int(D), _ptr(blob), int(nbytes))
     _cabi.check(st, "chain_b200_den_prepare")
-    blob_dev = blob.to(device) if torch.device(device).type == "cuda" else None
-    prep = PreparedDenGraph(blob, blob_dev, S, K, int(D))
+    copies = int(os.environ.get("CHAIN_B200_BLOB_COPIES", "8"))
+    blob_dev = blob.to(device).repeat(copies) if torch.device(device).type == "cuda" else None
+    prep = PreparedDenGraph(blob, blob_dev, copies, S, K, int(D))
     _prepared_cache[key] = (rows, prep)
     while len(_prepared_cache) > 8:
         _prepared_cache.popitem(last=False)
@@ -197,7 +199,7 @@ def _run_den_shared(prep, x, lengths, leaky_coefficient, flags):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     st = lib.chain_b200_den_forward_backward(
-        _ptr(prep.blob_host), _ptr(prep.blob_dev), _ptr(x), _ptr(ldev), B, T, D, float(leaky_coefficient), flags,
+        _ptr(prep.blob_host), _ptr(prep.blob_dev), prep.copies, _ptr(x), _ptr(ldev), B, T, D, float(leaky_coefficient), flags,
         _ptr(objf), _ptr(logp), _ptr(grad), _ptr(ok), _ptr(diag), _ptr(ws), ws_bytes, dev.index or 0, stream)
     _cabi.check(st, "chain_b200_den_forward_backward")
     _launches += lib.chain_b200_last_launch_count()

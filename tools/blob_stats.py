@@ -12,7 +12,7 @@ def stats(cfg, variant="uniform"):
     h = prep.blob_host.numpy()
     off = 40; out = []
     for i in range(3):
-        v = struct.unpack_from("<4i8q", h, off); off += 80; out.append(v)
+        v = struct.unpack_from("<4i5q", h, off); off += 56; out.append(v)
     tail = struct.unpack_from("<4q6d", h, off)
     print(f"{cfg} {variant}: pack {dt:.2f}s; " + "; ".join(
         f"view{i}: slices {out[i][1]} split {out[i][2]} recs {out[i][4]} wf {tail[4+i]:.0f}/{tail[7+i]:.0f}={tail[4+i]/tail[7+i]:.3f}" for i in range(3)))
