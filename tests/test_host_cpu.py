@@ -1,0 +1,240 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol of
+include/chain_b200.h, the graph containers mirror the reference's layout, the
+denominator packer is a loss-less re-arrangement of the arcs, argument checking
+and error behaviour.  No kernel is launched here."""
+import ctypes
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+import pychain_b200
+from pychain_b200 import ChainGraph, ChainGraphBatch, ChainFunction, Fst, synth, engine, _cabi
+from pychain_b200 import pychain_C as new_C
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "chain_b200.h")).read()
+    declared = set(re.findall(r"\b(chain_b200_[a-z_]+)\s*\(", hdr))
+    assert declared == set(_cabi.SIGNATURES), declared ^ set(_cabi.SIGNATURES)
+    lib = _cabi.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.chain_b200_version() >= 100
+    assert b"workspace" in lib.chain_b200_status_string(-2)
+    lib.chain_b200_set_verbose_level(2)
+    assert lib.chain_b200_get_verbose_level() == 2
+    lib.chain_b200_set_verbose_level(0)
+    assert lib.chain_b200_workspace_bytes(4, 10, 8, 5, 9, 0) > 4 * 11 * 5 * 4
+    assert lib.chain_b200_workspace_bytes(0, 10, 8, 5, 9, 0) == 0
+
+
+def test_pychain_surface_matches_reference_names():
+    for n in ("ChainLoss", "ChainFunction", "ChainGraph", "ChainGraphBatch"):
+        assert hasattr(pychain_b200, n)
+    for n in ("forward_backward", "forward_backward_log_domain", "set_verbose_level"):
+        assert callable(getattr(new_C, n))
+    import inspect
+    sig = list(inspect.signature(new_C.forward_backward).parameters)
+    assert sig == ["forward_transitions", "forward_transition_indices", "forward_transition_probs",
+                   "backward_transitions", "backward_transition_indices", "backward_transition_probs",
+                   "leaky_probs", "initial_probs", "final_probs", "start_state", "exp_nnet_output",
+                   "batch_sizes", "sequence_lengths", "num_states", "leaky_hmm_coefficient"]  # pychain.cc:26-41
+    assert len(inspect.signature(new_C.forward_backward_log_domain).parameters) == 13  # pychain.cc:81-94
+
+
+def test_no_cpu_fallback():
+    g = ChainGraph(synth.random_den_fst(10, 20, 16, seed=1))
+    gb = ChainGraphBatch(g, 2)
+    x, lengths = synth.make_inputs(2, 5, 16, seed=2)
+    with pytest.raises(_cabi.ChainB200Error, match="no CPU fallback"):
+        ChainFunction.apply(x, lengths, gb, 1e-5)
+    with pytest.raises(_cabi.ChainB200Error):
+        new_C.forward_backward(gb.forward_transitions, gb.forward_transition_indices, gb.forward_transition_probs,
+                               gb.backward_transitions, gb.backward_transition_indices, gb.backward_transition_probs,
+                               gb.leaky_probs, gb.initial_probs, gb.final_probs, gb.start_state,
+                               x.exp(), None, lengths, gb.num_states, 1e-5)
+
+
+def test_chain_function_error_behaviour():
+    g = ChainGraph(synth.random_den_fst(10, 20, 16, seed=1))
+    x, _ = synth.make_inputs(3, 5, 16, seed=2)
+    with pytest.raises(ValueError, match="does not equal to graph batch size"):  # loss.py:32-36
+        ChainFunction.apply(x, torch.tensor([5, 5, 5]), ChainGraphBatch(g, 2), 1e-5)
+    with pytest.raises(RuntimeError, match="sorted in decreasing order"):        # pack_padded_sequence, loss.py:37-39
+        ChainFunction.apply(x, torch.tensor([3, 5, 4]), ChainGraphBatch(g, 3), 1e-5)
+    with pytest.raises(RuntimeError, match="greater than 0"):
+        ChainFunction.apply(x, torch.tensor([5, 3, 0]), ChainGraphBatch(g, 3), 1e-5)
+    with pytest.raises(ValueError, match="batch size should be specified"):      # graph.py:76-77
+        ChainGraphBatch(g)
+    with pytest.raises(ValueError, match="max_num_transitions"):                 # graph.py:81-85
+        ChainGraphBatch([g, g])
+
+
+def test_fst_to_tensors_layout():
+    """fstext.cc:19-117 semantics: forward CSR by source, backward CSR by destination (stable)."""
+    #        src dst pdf  logw
+    arcs = [(0, 1, 3, -0.5), (0, 2, 1, -1.0), (1, 2, 0, -0.2), (2, 0, 2, -0.7), (1, 1, 4, -0.9)]
+    fst = Fst(3, 0, [a[0] for a in arcs], [a[1] for a in arcs], [a[2] for a in arcs], [a[3] for a in arcs],
+              [-np.inf, -np.inf, -0.1])
+    g = ChainGraph(fst)
+    assert g.forward_transitions.tolist() == [[0, 1, 3], [0, 2, 1], [1, 2, 0], [1, 1, 4], [2, 0, 2]]
+    assert g.forward_transition_indices.tolist() == [[0, 2], [2, 4], [4, 5]]
+    assert g.backward_transitions.tolist() == [[2, 0, 2], [0, 1, 3], [1, 1, 4], [0, 2, 1], [1, 2, 0]]
+    assert g.backward_transition_indices.tolist() == [[0, 1], [1, 3], [3, 5]]
+    assert torch.allclose(g.forward_transition_probs, torch.tensor([-0.5, -1.0, -0.2, -0.9, -0.7]).exp())
+    assert g.forward_transitions.dtype == torch.int32 and g.forward_transition_probs.dtype == torch.float32
+    assert torch.allclose(g.final_probs, torch.tensor([0.0, 0.0, np.exp(-0.1)], dtype=torch.float32))
+    assert g.initial_probs.tolist() == [1.0, 0.0, 0.0] and abs(g.leaky_probs.sum().item() - 1.0) < 1e-5
+    gl = ChainGraph(fst, log_domain=True, final_mode="ones")
+    assert gl.leaky_probs is None and gl.initial_probs[0] == 0 and torch.isneginf(gl.initial_probs[1:]).all()
+    assert gl.final_probs.tolist() == [0.0, 0.0, 0.0]
+    # text format round trip (fstprint): weights are costs, ilabel = pdf + 1
+    txt = ["0 1 4 4 0.5", "0 2 2 2 1.0", "1 2 1 1 0.2", "2 0 3 3 0.7", "1 1 5 5 0.9", "2 0.1"]
+    g2 = ChainGraph(Fst.from_text(txt))
+    assert torch.equal(g2.forward_transitions, g.forward_transitions)
+    assert torch.allclose(g2.forward_transition_probs, g.forward_transition_probs)
+
+
+def test_leaky_probs_power_method():
+    """fstext.cc:120-171: 100 iterations of the per-state-normalised HMM, averaged."""
+    fst = synth.random_den_fst(12, 40, 5, seed=3)
+    S = 12
+    w = np.exp(fst.log_weight.astype(np.float64))
+    nf = 1.0 / (np.exp(fst.final_log_weight.astype(np.float64)) + np.bincount(fst.src, weights=w, minlength=S))
+    cur = np.zeros(S); cur[0] = 1.0; avg = np.zeros(S)
+    for _ in range(100):
+        avg += cur / 100
+        nxt = np.zeros(S)
+        for s, d, ww in zip(fst.src, fst.dst, w):
+            nxt[d] += cur[s] * nf[s] * ww
+        cur = nxt / nxt.sum()
+    assert np.abs(fst.leaky_probs().numpy() - avg.astype(np.float32)).max() < 1e-7
+
+
+def test_graph_batch_layouts_and_reorder():
+    g = ChainGraph(synth.random_den_fst(10, 20, 16, seed=1))
+    gb = ChainGraphBatch(g, 5)
+    assert gb.forward_transitions.shape == (5, 20, 3) and gb.forward_transitions.stride(0) == 0
+    assert gb.leaky_probs.shape == (5, 10) and gb.start_state.tolist() == [0] * 5
+    gb.reorder(torch.tensor([4, 3, 2, 1, 0]))
+    assert gb.forward_transitions.stride(0) == 0
+    gm = ChainGraphBatch(g, 3).materialize()
+    assert gm.forward_transitions.is_contiguous() and gm.shared_graph is None
+    nb = synth.make_num_batch(4, 40, 16, seed=5, min_phones=3, max_phones=6)
+    assert nb.log_domain and nb.leaky_probs is None
+    assert torch.isneginf(nb.initial_probs).any() and nb.forward_transitions.shape[0] == 4
+    first = nb.forward_transition_probs[0].clone()
+    nb.reorder(torch.tensor([1, 0, 2, 3]))
+    assert torch.equal(nb.forward_transition_probs[1], first)
+
+
+def _parse_blob(blob):
+    h = blob.numpy().tobytes()
+    magic, version, S, K, D, nw, S_pad, D_pad, max_sub, _ = struct.unpack_from("<II8i", h, 0)
+    views, off = [], 40
+    for i in range(3):
+        n_rows, n_slices, n_split, n_sub, n_recs, o_info, o_rows, o_recs, o_split = struct.unpack_from("<4i5q", h, off)
+        off += 56
+        info = np.frombuffer(h, np.int64, nw * 3, o_info).reshape(nw, 3)
+        rows = np.frombuffer(h, np.int32, (n_slices + 3 * nw) * 32, o_rows)
+        recs = np.frombuffer(h, np.uint32, n_recs * 2, o_recs).reshape(-1, 2)
+        split = np.frombuffer(h, np.int32, n_split * 3, o_split).reshape(-1, 3)
+        views.append(dict(n_rows=n_rows, n_slices=n_slices, n_sub=n_sub, info=info, rows=rows, recs=recs, split=split))
+    o_leaky, o_init, o_final, total = struct.unpack_from("<4q", h, off)
+    pred = struct.unpack_from("<6d", h, off + 32)
+    return dict(S=S, K=K, D=D, nw=nw, max_sub=max_sub, views=views, total=total, pred=pred,
+                leaky=np.frombuffer(h, np.float32, S, o_leaky), final=np.frombuffer(h, np.float32, S, o_final))
+
+
+def _decode_view(v, nw):
+    """Walk the per-warp streams exactly like sell_pass does: returns {(row, a, b, w_bits) multiset}."""
+    out = []
+    sub_owner = {}
+    for row, first, cnt in v["split"]:
+        for j in range(cnt):
+            sub_owner[first + j] = row
+    slices_seen = 0
+    for w in range(nw):
+        rec0, npairs, row0 = v["info"][w]
+        assert npairs % 2 == 0
+        rp = row0
+        pending = [[] for _ in range(32)]
+        for j in range(npairs):
+            for half in range(2):
+                blk = v["recs"][rec0 + (2 * j + half) * 32: rec0 + (2 * j + half) * 32 + 32]
+                for lane in range(32):
+                    ab, wb = int(blk[lane, 0]), int(blk[lane, 1])
+                    wt = np.frombuffer(np.uint32(wb & 0x7fffffff).tobytes(), np.float32)[0]
+                    if wt != 0.0:
+                        pending[lane].append((ab & 0xffff, ab >> 16, wt))
+                if half == 1:
+                    flags = (blk[:, 1] >> 31) & 1
+                    assert flags.min() == flags.max(), "end-of-slice flag must be warp-uniform"
+                    if flags[0]:
+                        codes = v["rows"][rp: rp + 32]
+                        rp += 32
+                        slices_seen += 1
+                        for lane in range(32):
+                            code = int(codes[lane])
+                            row = code if code >= 0 else (sub_owner[-2 - code] if code <= -2 else None)
+                            assert row is not None or not pending[lane]
+                            out += [(row,) + t for t in pending[lane]]
+                            pending[lane] = []
+        assert not any(pending)
+    assert slices_seen == v["n_slices"]
+    return sorted(out)
+
+
+@pytest.mark.parametrize("variant,S,K,D", [("uniform", 70, 400, 24), ("skew", 90, 1500, 16)])
+def test_den_packer_is_lossless(variant, S, K, D):
+    g = ChainGraph(synth.random_den_fst(S, K, D, seed=9, variant=variant))
+    gb = ChainGraphBatch(g, 2)
+    gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_PROB)
+    engine._prepared_cache.clear()
+    prep = engine.prepare_den_graph(gt, g.num_states, D, "cpu")
+    b = _parse_blob(prep.blob_host)
+    assert (b["S"], b["K"], b["D"], b["nw"]) == (S, K, D, 16) and b["total"] == prep.blob_host.numel()
+    ft, fp = g.forward_transitions.numpy(), g.forward_transition_probs.numpy()
+    want = [
+        sorted((int(d), int(s), int(n), np.float32(p)) for (s, d, n), p in zip(ft, fp)),   # alpha: row=dst, a=src, b=pdf
+        sorted((int(s), int(d), int(n), np.float32(p)) for (s, d, n), p in zip(ft, fp)),   # beta:  row=src, a=dst, b=pdf
+        sorted((int(n), int(s), int(d), np.float32(p)) for (s, d, n), p in zip(ft, fp)),   # gamma: row=pdf, a=src, b=dst
+    ]
+    for i in range(3):
+        got = _decode_view(b["views"][i], 16)
+        assert len(got) == K
+        assert [(r, a, bb) for r, a, bb, _ in got] == [(r, a, bb) for r, a, bb, _ in want[i]]
+        assert np.allclose(sorted(w for *_, w in got), sorted(w for *_, w in want[i]))
+    if variant == "skew":
+        assert b["views"][0]["n_sub"] > 0 and b["max_sub"] >= b["views"][0]["n_sub"]
+    assert np.array_equal(b["leaky"], g.leaky_probs.numpy())
+    # the packer's bank-conflict model improves on the unarranged order and is >= the ideal
+    assert all(b["pred"][i] >= b["pred"][3 + i] for i in range(3))
+    os.environ["CHAIN_B200_PACK_EFFORT"] = "0"
+    try:
+        engine._prepared_cache.clear()
+        base = _parse_blob(engine.prepare_den_graph(gt, g.num_states, D, "cpu").blob_host)
+    finally:
+        os.environ.pop("CHAIN_B200_PACK_EFFORT")
+        engine._prepared_cache.clear()
+    assert sum(b["pred"][:3]) < sum(base["pred"][:3])
+
+
+def test_den_packer_rejects_bad_graphs():
+    lib = _cabi.lib()
+    g = ChainGraph(synth.random_den_fst(10, 30, 8, seed=1))
+    ft, fi, bt, bi = (g.forward_transitions.clone(), g.forward_transition_indices.clone(),
+                      g.backward_transitions.clone(), g.backward_transition_indices.clone())
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert lib.chain_b200_den_prepare_bytes(p(ft), p(fi), p(bt), p(bi), 10, 30, 8) > 0
+    assert lib.chain_b200_den_prepare_bytes(p(ft), p(fi), p(bt), p(bi), 10, 30, 4) == _cabi.ERR_INVALID_ARG  # pdf out of range
+    bad = ft.clone(); bad[3, 1] = 99
+    assert lib.chain_b200_den_prepare_bytes(p(bad), p(fi), p(bt), p(bi), 10, 30, 8) == _cabi.ERR_INVALID_ARG
+    assert lib.chain_b200_den_prepare_bytes(p(ft), p(fi), p(bt), p(bi), 70000, 30, 8) == _cabi.ERR_UNSUPPORTED
+    assert lib.chain_b200_den_workspace_bytes(p(torch.zeros(512, dtype=torch.uint8)), 4, 10) == 0  # not a blob
