@@ -583,7 +583,9 @@ static int choose_G(const BlobHeader &h, int B, int num_sms) {
     const int g = atoi(env);
     if ((g == 1 || g == 2 || g == 4) && den_smem_bytes(h, g) <= 227 * 1024) return g;
   }
-  const double cost[5] = {0, 0.36, 0.62, 0, 1.0};
+  // measured on B200 (cfg4): a frame of a G-group costs nearly the same for every G (the gathers are
+  // wavefront-bound, not byte-bound), so minimise the number of rounds first, then prefer the smaller G
+  const double cost[5] = {0, 0.84, 0.88, 0, 1.0};
   int best = 0;
   double best_t = 1e30;
   for (int g : {4, 2, 1}) {

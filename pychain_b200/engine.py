@@ -172,7 +172,7 @@ def prepare_den_graph(graph_tensors, num_states, D, device):
         torch.empty(int(nbytes), dtype=torch.uint8)
     st = lib.chain_b200_den_prepare(*[_ptr(t) for t in host], S, K, int(D), _ptr(blob), int(nbytes))
     _cabi.check(st, "chain_b200_den_prepare")
-    copies = int(os.environ.get("CHAIN_B200_BLOB_COPIES", "8"))
+    copies = int(os.environ.get("CHAIN_B200_BLOB_COPIES", "1"))
     blob_dev = blob.to(device).repeat(copies) if torch.device(device).type == "cuda" else None
     prep = PreparedDenGraph(blob, blob_dev, copies, S, K, int(D))
     _prepared_cache[key] = (rows, prep)
