@@ -110,30 +110,50 @@ def make_workload(cfg, variant, rank):
 
 
 # ------------------------------------------------------------------ reference CPU arm / cpu_baseline
+def mode_of(cfg):
+    """cfg2 is the leaky-free denominator through the LOG-domain entry (BASELINE.json configs[1]),
+    cfg3 the full ChainLoss (numerator + denominator, forward + backward); the rest are the
+    probability-domain denominator."""
+    return {"cfg2": "logden", "cfg3": "loss"}.get(cfg, "den")
+
+
 def _ref_worker(args):
     """One host process: the reference extension's CPU path on a shard."""
     cfg, variant, start, count, reps = args
     import torch
     torch.set_num_threads(1)
-    from pychain_b200 import synth, ChainGraphBatch
+    from pychain_b200 import synth, ChainGraph, ChainGraphBatch
     from oracle import chain_oracle as co
     c = synth.CONFIGS[cfg]
-    graph = synth.den_graph_for(cfg, variant=variant)
+    mode = mode_of(cfg)
     x, _ = synth.make_inputs(count, c["T"], c["D"], seed=4000 + start)
     lengths = torch.full((count,), c["T"], dtype=torch.long)
-    ex = x.clamp(-30, 30).exp()
-    gb = ChainGraphBatch(graph, count).materialize()
+    xc = x.clamp(-30, 30)
     use_ref = co.ref_available()
+    if mode == "logden":
+        lg = ChainGraph(synth.random_den_fst(c["S"], c["K"], c["D"], seed=1002), log_domain=True)
+        lgb = ChainGraphBatch(lg, count).materialize()
+    else:
+        graph = synth.den_graph_for(cfg, variant=variant)
+        gb = ChainGraphBatch(graph, count).materialize()
+        ex = xc.exp()
+    if mode == "loss":
+        nb = synth.make_num_batch(count, c["T"], c["D"], seed=52 + start)
     out = []
+    objf = 0.0
     for _ in range(reps):
         t0 = time.perf_counter()
-        if use_ref:
-            objf, grad, ok = co.den_ref(gb, ex, lengths, 1e-5)
-            objf = float(objf)
+        if mode == "logden":
+            o = co.num_ref(lgb, xc, lengths)[0] if use_ref else co.num_c(lgb, xc, lengths)[0]
+            objf = float(o)
         else:
-            objf, _, grad, ok, _ = co.den_c(gb, ex, lengths, 1e-5)
+            o = co.den_ref(gb, ex, lengths, 1e-5)[0] if use_ref else co.den_c(gb, ex, lengths, 1e-5)[0]
+            objf = float(o)
+            if mode == "loss":
+                o2 = co.num_ref(nb, xc, lengths)[0] if use_ref else co.num_c(nb, xc, lengths)[0]
+                objf -= float(o2)
         out.append(time.perf_counter() - t0)
-    return out, float(objf), "reference" if use_ref else "port"
+    return out, objf, "reference" if use_ref else "port"
 
 
 def cpu_reference_run(cfg, variant, sample, reps, max_workers=None):
@@ -161,7 +181,7 @@ def run_reference_arm(a):
         return
     from pychain_b200 import synth
     c = synth.CONFIGS[a.config]
-    per_seq_s = 2.0 * c["K"] * c["T"] / 3.4e8  # BASELINE.md cost model, one core
+    per_seq_s = 2.0 * c["K"] * c["T"] / (3.0e7 if mode_of(a.config) == "logden" else 3.4e8)  # BASELINE.md cost model, one core
     cores = min(os.cpu_count() or 1, 64)
     sample = a.cpu_sample or max(cores, min(c["B"], int(cores * 2.0 / per_seq_s) or 1))
     sample = min(sample, c["B"])
@@ -183,8 +203,10 @@ def run_reference_arm(a):
 
 
 def workload_name(cfg, variant, c):
-    return "%s: den fwd+bwd, S=%d states K=%d arcs (%s random FST), B=%d/GPU T=%d D=%d, leaky=1e-5" % (
-        cfg, c["S"], c["K"], variant, c["B"], c["T"], c["D"])
+    what = {"den": "den fwd+bwd, leaky=1e-5", "logden": "leaky-free den fwd+bwd through the log-domain entry",
+            "loss": "full ChainLoss (per-utterance numerators + den, leaky=1e-5) fwd+bwd, variable T"}[mode_of(cfg)]
+    return "%s: %s, S=%d states K=%d arcs (%s random FST), B=%d/GPU T=%d D=%d" % (
+        cfg, what, c["S"], c["K"], variant, c["B"], c["T"], c["D"])
 
 
 # ------------------------------------------------------------------ main arm
@@ -210,15 +232,47 @@ def main():
 
     c, graph, x_host, lengths = make_workload(a.config, a.variant, rank)
     B, T, D, S, K = c["B"], c["T"], c["D"], c["S"], c["K"]
+    mode = mode_of(a.config)
+    from pychain_b200 import ChainGraph, ChainLoss
+    if mode == "logden":
+        graph = ChainGraph(synth.random_den_fst(S, K, D, seed=1002), log_domain=True)
     gb = ChainGraphBatch(graph, B)
-    gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_PROB)
+    gt = tuple(getattr(gb, n) for n in (engine._GRAPH_NAMES_LOG if mode == "logden" else engine._GRAPH_NAMES_PROB))
     x_dev = x_host.to(dev)
     x_pin = x_host.pin_memory()
     frames = int(lengths.sum())
     stats = torch.zeros(3, dtype=torch.float32, device=dev)
+    if mode == "loss":
+        num_batch = synth.make_num_batch(B, T, D, seed=52 + 1000 * rank)
+        crit = ChainLoss(graph, 1e-5, avg=False)
+        kernel_name = "den_shared_kernel + chain_generic_kernel<log>"
+    else:
+        kernel_name = "chain_generic_kernel<log>" if mode == "logden" else "den_shared_kernel"
+
+    class _R(object):
+        pass
+
+    def run_engine(xt):
+        """One step on a device-resident input; returns an object with .objf and .ok (device tensors)."""
+        if mode == "den":
+            return engine.forward_backward_prob(gt, xt, lengths, S, 1e-5, x_is_exp=False, clamp=True)
+        if mode == "logden":
+            return engine.forward_backward_log(gt, xt, lengths, S, grad_as_log=False, clamp=True)
+        xg = xt.detach().requires_grad_(True)
+        loss = crit(xg, lengths, num_batch)
+        loss.backward()
+        r = _R()
+        r.objf, r.ok = loss.detach(), ChainFunction.last_ok
+        return r
+
+    def run_api(xt):
+        """The call a user makes (public API) on a staged input; returns the step's scalar result."""
+        if mode == "loss":
+            return run_engine(xt).objf
+        return ChainFunction.apply(xt, lengths, gb, 1e-5) if mode == "den" else ChainFunction.apply(xt, lengths, gb)
 
     def step_resident():
-        r = engine.forward_backward_prob(gt, x_dev, lengths, S, 1e-5, x_is_exp=False, clamp=True)
+        r = run_engine(x_dev)
         if world > 1:  # the single collective of the sharded loss: sum of {objf, frames, not ok}
             stats[0] = r.objf
             stats[1] = float(frames)
@@ -247,7 +301,7 @@ def main():
     e0.record()
     for i in range(a.steps):
         kern_ev[i][0].record()
-        r = engine.forward_backward_prob(gt, x_dev, lengths, S, 1e-5, x_is_exp=False, clamp=True)
+        r = run_engine(x_dev)
         kern_ev[i][1].record()
         if world > 1:
             stats[0] = r.objf
@@ -272,7 +326,6 @@ def main():
     # -------- e2e: public API, pinned host input -> H2D, objf -> D2H, every step.
     # The H2D copy of step i+1 is issued on a copy stream while step i computes (two staging
     # buffers), as a training loop's prefetcher would; every step's copy is inside the timed region.
-    den_batch = ChainGraphBatch(graph, B)
     stage = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     copy_stream = torch.cuda.Stream(device=dev)
@@ -290,7 +343,7 @@ def main():
             if i + 1 < n:
                 issue_copy(i + 1)  # buffer (i+1)%2 was last read by step i-1, which .item() below has drained
             main_stream.wait_event(ready[i % 2])
-            o = ChainFunction.apply(stage[i % 2], lengths, den_batch, 1e-5)
+            o = run_api(stage[i % 2])
             if world > 1:
                 stats[0] = o
                 stats[1] = float(frames)
@@ -328,6 +381,8 @@ def main():
         except Exception:
             pass
     alg_bytes = frames * (12.0 * D + 8.0 * S)
+    if mode == "loss":
+        alg_bytes += frames * (12.0 * D + 8.0 * num_batch.num_states)
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -337,14 +392,14 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "den_shared_kernel", "kernel_ms": kern_ms,
+                "traffic": traffic, "kernel": kernel_name, "kernel_ms": kern_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "note": "algorithmic bytes = F*(12D+8S); the kernel is shared-memory-gather bound, see DESIGN.md"}
+                "note": "algorithmic bytes = F*(12D+8S) (x2 for the full loss: numerator + denominator); the kernels are shared-memory-gather / latency bound, see DESIGN.md"}
 
     cpu_baseline = None
     if not a.no_cpu_baseline and world == 1:
         try:
-            per_seq_s = 2.0 * K * T / 3.4e8
+            per_seq_s = 2.0 * K * T / (3.0e7 if mode == "logden" else 3.4e8)
             cores = min(os.cpu_count() or 1, 64)
             sample = a.cpu_sample or max(cores, min(B, int(cores * 4.0 / per_seq_s) or 1))
             sample = min(sample, B)
@@ -365,7 +420,7 @@ def main():
                        B * T * D * 4 / 1e6, B * (T + 1) * S * 4 / 1e6)},
         "objf": objf, "ok": ok,
         "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": B * T * D * 4,
-                "d2h_bytes_per_step": 4, "api": "pychain_b200.ChainFunction.apply; pinned host x -> device every step (copy of step i+1 overlaps step i), objf.item() every step"},
+                "d2h_bytes_per_step": 4, "api": "pychain_b200.%s; pinned host x -> device every step (copy of step i+1 overlaps step i), objf.item() every step" % ("ChainLoss.forward + backward" if mode == "loss" else "ChainFunction.apply")},
         "gpu_launches": launches,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
     }

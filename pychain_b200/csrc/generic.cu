@@ -24,7 +24,6 @@ namespace chainb200 {
 thread_local int g_launch_count = 0;
 int g_verbose_level = 0;
 
-constexpr int GEN_NT = 256;
 
 struct GenericParams {
   const int32_t *ft, *fi, *bt, *bi;
@@ -116,7 +115,9 @@ __device__ __forceinline__ float load_x(const float *__restrict__ p, unsigned fl
   return v;
 }
 
-template <bool LOG>
+// NT threads per CTA: 128 for small per-utterance graphs (numerators; cheap barriers),
+// 1024 for graphs with hundreds of states (one state per thread).
+template <bool LOG, int GEN_NT>
 __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericParams p) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float scratch[64];
@@ -445,12 +446,15 @@ static int run_generic(const int32_t *ft, const int32_t *fi, const float *fp, co
   p.pdf_ptr = (const int32_t *)(base + w.pdf_ptr);
   p.pdf_rec = (const uint2 *)(base + w.pdf_rec);
 
-  auto kern = chain_generic_kernel<LOG>;
+  const int nt = (S <= 160) ? 128 : (S <= 448 ? 256 : 1024);
+  void (*kern)(const GenericParams) = chain_generic_kernel<LOG, 256>;
+  if (nt == 128) kern = chain_generic_kernel<LOG, 128>;
+  if (nt == 1024) kern = chain_generic_kernel<LOG, 1024>;
   if (smem > 48 * 1024) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  kern<<<B, GEN_NT, smem, stream>>>(p);
+  kern<<<B, nt, smem, stream>>>(p);
   g_launch_count++;
   launch_finalize(p.logp, p.diag, B, LOG ? 0 : 1, objf, ok, diag, stream);
   g_launch_count++;
