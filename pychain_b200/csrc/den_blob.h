@@ -26,7 +26,10 @@ namespace chainb200 {
 
 constexpr uint32_t kBlobMagic = 0x42324348u;  // "HC2B"
 constexpr uint32_t kBlobVersion = 6;
-constexpr int DEN_NW = 16;           // warps per CTA the slice schedule is built for
+#ifndef CHAIN_B200_NW
+#define CHAIN_B200_NW 16
+#endif
+constexpr int DEN_NW = CHAIN_B200_NW;           // warps per CTA the slice schedule is built for
 constexpr int DEN_NT = DEN_NW * 32;
 #ifndef CHAIN_B200_FIFO_PAIRS
 #define CHAIN_B200_FIFO_PAIRS 4

@@ -351,10 +351,10 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
     }
     rows_seq.insert(rows_seq.end(), 3 * 32, -1);  // the row prefetch runs slices ahead
     size_t pairs = (v.rec_ab.size() - rec0) / 64;
-    const size_t run = (pairs + 2 * kFifoPairs - 1) / (2 * kFifoPairs) * (2 * kFifoPairs);
+    const size_t run = pairs;  // the kernel runs the last (partial) double bank through a predicated tail
     v.warp_info[3 * wv + 1] = (int64_t)run;
-    v.rec_ab.insert(v.rec_ab.end(), (run - pairs + kFifoPairs) * 64, 0u);  // idle pairs + FIFO run-out
-    v.rec_w.insert(v.rec_w.end(), (run - pairs + kFifoPairs) * 64, 0.f);
+    v.rec_ab.insert(v.rec_ab.end(), (size_t)3 * kFifoPairs * 64, 0u);  // register-bank run-out
+    v.rec_w.insert(v.rec_w.end(), (size_t)3 * kFifoPairs * 64, 0.f);
   }
   v.rows.swap(rows_seq);
 }

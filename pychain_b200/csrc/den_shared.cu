@@ -171,7 +171,8 @@ __device__ __forceinline__ void sell_pass(const DView &v, const float *__restric
       rp += 32;
     }
   };
-  for (int j = 0; j < npairs; j += 2 * kFifoPairs) {
+  int j = 0;
+  for (; j + 2 * kFifoPairs <= npairs; j += 2 * kFifoPairs) {  // full double banks: straight-line code
 #pragma unroll
     for (int d = 0; d < kFifoPairs; d++) {
       fb[d][0] = ldg_stream(sp + (2 * d) * 32);
@@ -188,6 +189,24 @@ __device__ __forceinline__ void sell_pass(const DView &v, const float *__restric
     sp += 2 * kFifoPairs * 32;
 #pragma unroll
     for (int d = 0; d < kFifoPairs; d++) process(fb[d][0], fb[d][1]);
+  }
+  const int rem = npairs - j;  // < 2*kFifoPairs pairs left: bank A holds the first kFifoPairs of them
+  if (rem > 0) {
+    if (rem > kFifoPairs) {
+#pragma unroll
+      for (int d = 0; d < kFifoPairs; d++) {
+        fb[d][0] = ldg_stream(sp + (2 * d) * 32);
+        fb[d][1] = ldg_stream(sp + (2 * d + 1) * 32);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < kFifoPairs; d++)
+      if (d < rem) process(fa[d][0], fa[d][1]);
+    if (rem > kFifoPairs) {
+#pragma unroll
+      for (int d = 0; d < kFifoPairs; d++)
+        if (kFifoPairs + d < rem) process(fb[d][0], fb[d][1]);
+    }
   }
 }
 

@@ -162,7 +162,6 @@ def _decode_view(v, nw):
     slices_seen = 0
     for w in range(nw):
         rec0, npairs, row0 = v["info"][w]
-        assert npairs % 2 == 0
         rp = row0
         pending = [[] for _ in range(32)]
         for j in range(npairs):
