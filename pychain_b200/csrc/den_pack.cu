@@ -67,9 +67,13 @@ struct Rng {
   double unit() { return next() * (1.0 / 4294967296.0); }
 };
 
-static int pack_effort() {
+// Search effort of the packer: 0 = plain degree-sorted SELL, >= 1 = conflict-aware.  The graph is
+// packed once per training run, so the default spends ~1 s on a 40k-arc graph and scales back
+// for very large graphs.
+static int pack_effort(int K) {
   const char *e = getenv("CHAIN_B200_PACK_EFFORT");
-  return e ? std::max(0, atoi(e)) : 2;
+  if (e) return std::max(0, atoi(e));
+  return K <= 120000 ? 4 : (K <= 400000 ? 2 : 1);
 }
 
 // A. Regroup the (length-sorted) units so that every run of 8 consecutive units -- the rows a
@@ -95,6 +99,9 @@ static void balance_quarters(const std::vector<Unit> &units, std::vector<int> &o
     long sum[16];
     for (int c = 0; c < 16; c++) sum[c] = hist[first][c];
     const size_t len0 = units[first].arcs.size();
+    // bank groups already taken by the output rows of this quarter (the epilogue stores out[row][g])
+    auto out_group = [&](int u) { const int c = units[u].row_code; return (c >= 0 ? c : -2 - c) & 7; };  // row or partial slot
+    unsigned out_used = 1u << out_group(first);
     for (int pick = 1; pick < 8 && (int)out.size() < n; pick++) {
       int best = -1;
       long best_cost = 0;
@@ -108,11 +115,13 @@ static void balance_quarters(const std::vector<Unit> &units, std::vector<int> &o
         long cost = 0;
         for (int c = 0; c < 16; c++) { const long t = sum[c] + hist[u][c]; cost += t * t; }
         cost = cost * 4 + (long)(len0 - units[u].arcs.size()) * 64;
+        if ((out_used >> out_group(u)) & 1u) cost += 24;
         if (best < 0 || cost < best_cost) { best = j; best_cost = cost; }
       }
       if (best < 0) break;
       used[best] = 1;
       out.push_back(order[best]);
+      out_used |= 1u << out_group(order[best]);
       for (int c = 0; c < 16; c++) sum[c] += hist[order[best]][c];
     }
   }
@@ -212,7 +221,7 @@ static void arrange_slice(const std::vector<const Unit *> &lanes, int width, std
 static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, const std::vector<uint32_t> &ab,
                        const float *w, int n_a, int n_b, bool structure_only, ViewBuild &v) {
   v.n_rows = n_rows;
-  const int effort = pack_effort();
+  const int effort = pack_effort(K);
   Rng rng(0xC0FFEEull + (uint64_t)n_rows * 7919u + (uint64_t)K);
   // rows -> arc lists, arc order inside a row = CSR order (the reference's summation order)
   std::vector<int32_t> deg(n_rows, 0);
