@@ -14,6 +14,8 @@ and a shared denominator graph is packed once and kept on the device instead
 of being replicated B times on the host and uploaded per call (loss.py:99,
 graph.py:101-120, chain-computation.cc:77-89).
 """
+import threading
+
 import torch
 import torch.nn as nn
 
@@ -21,6 +23,8 @@ from .graph import ChainGraphBatch
 from . import engine
 
 __all__ = ["ChainFunction", "ChainLoss"]
+
+_tls = threading.local()
 
 
 def _check_lengths(input, input_lengths):
@@ -54,13 +58,29 @@ class ChainFunction(torch.autograd.Function):
                 .format(B, graphs.batch_size)
             )
         lengths = _check_lengths(input, input_lengths)
-        if not graphs.log_domain:  # usually for the denominator
-            g = tuple(getattr(graphs, n) for n in engine._GRAPH_NAMES_PROB)
-            r = engine.forward_backward_prob(g, input, lengths, graphs.num_states, leaky_coefficient,
-                                             x_is_exp=False, clamp=True)
-        else:  # usually for the numerator
+
+        def run():
+            if not graphs.log_domain:  # usually for the denominator
+                g = tuple(getattr(graphs, n) for n in engine._GRAPH_NAMES_PROB)
+                return engine.forward_backward_prob(g, input, lengths, graphs.num_states, leaky_coefficient,
+                                                    x_is_exp=False, clamp=True)
+            # usually for the numerator
             g = tuple(getattr(graphs, n) for n in engine._GRAPH_NAMES_LOG)
-            r = engine.forward_backward_log(g, input, lengths, graphs.num_states, grad_as_log=False, clamp=True)
+            return engine.forward_backward_log(g, input, lengths, graphs.num_states, grad_as_log=False, clamp=True)
+
+        side = getattr(_tls, "side_stream", None)
+        if side is not None and input.is_cuda:
+            # launch on the side stream (ChainLoss overlaps numerator and denominator); the autograd
+            # node itself still belongs to the caller's stream, which joins `side` before using the results
+            main = torch.cuda.current_stream(input.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                r = run()
+            input.record_stream(side)
+            for t in (r.objf, r.grad, r.ok):
+                t.record_stream(main)
+        else:
+            r = run()
         ctx.save_for_backward(r.grad)
         ctx.mark_non_differentiable(r.ok)
         ChainFunction.last_ok = r.ok  # device int32[1]; not synchronised (the reference ignores `ok`, loss.py:44,62)
@@ -81,11 +101,29 @@ class ChainLoss(nn.Module):
         self.avg = avg
         self.leaky_coefficient = leaky_coefficient
 
+    # numerator and denominator are independent: the numerator kernels run on a side stream,
+    # concurrently with the denominator (they fit next to it / on the SMs it leaves idle)
+    overlap_streams = True
+    _side_streams = {}
+
     def forward(self, x, x_lengths, num_graphs):
         batch_size = x.size(0)
         den_graphs = ChainGraphBatch(self.den_graph, batch_size)  # stride-0 views: O(1), not a B-fold copy
-        den_objf = ChainFunction.apply(x, x_lengths, den_graphs, self.leaky_coefficient)
-        num_objf = ChainFunction.apply(x, x_lengths, num_graphs)
+        if self.overlap_streams and x.is_cuda:
+            main = torch.cuda.current_stream(x.device)
+            side = ChainLoss._side_streams.get(x.device)
+            if side is None:
+                side = ChainLoss._side_streams[x.device] = torch.cuda.Stream(device=x.device)
+            _tls.side_stream = side
+            try:
+                num_objf = ChainFunction.apply(x, x_lengths, num_graphs)  # kernels go to `side`
+            finally:
+                _tls.side_stream = None
+            den_objf = ChainFunction.apply(x, x_lengths, den_graphs, self.leaky_coefficient)
+            main.wait_stream(side)
+        else:
+            den_objf = ChainFunction.apply(x, x_lengths, den_graphs, self.leaky_coefficient)
+            num_objf = ChainFunction.apply(x, x_lengths, num_graphs)
         objf = -(num_objf - den_objf)
         if self.avg:
             objf = objf / x_lengths.sum()
