@@ -71,6 +71,15 @@ __device__ __forceinline__ void lse_merge(float &m, float &s, float m2, float s2
   s = s * expf(m - M) + s2 * expf(m2 - M);
   m = M;
 }
+// Running log-sum-exp: fold one term into (m, s) with a single exp.
+__device__ __forceinline__ void lse_add(float &m, float &s, float t) {
+  if (t > m) {
+    s = s * expf(m - t) + 1.f;  // m = -inf: exp(-inf) = 0
+    m = t;
+  } else if (t > -INFINITY) {
+    s += expf(t - m);
+  }
+}
 __device__ __forceinline__ float block_lse(float m, float s, float *scratch /* >= 64 floats */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll

@@ -36,7 +36,9 @@ struct GenericParams {
   float *logp, *grad, *diag;  // diag: [B][2]
   float *alpha_ws, *tot_ws;   // [B][T+1][S], [B][T+1]
   const int32_t *pdf_ptr;     // [Bg][D+1]
-  const uint2 *pdf_rec;       // [Bg][K]  {src | dst<<16, weight bits}
+  const uint2 *pdf_rec;       // [Bg][K]  {src | dst<<16, weight bits}   arcs sorted by pdf
+  const uint2 *bwd_rec;       // [Bg][K]  {src | pdf<<16, weight bits}   backward-CSR order (alpha pass)
+  const uint2 *fwd_rec;       // [Bg][K]  {dst | pdf<<16, weight bits}   forward-CSR order (beta pass)
 };
 
 // ---------------------------------------------------------------- pdf-sorted view
@@ -44,9 +46,13 @@ struct GenericParams {
 // smem: (D+1) ints.
 __global__ void __launch_bounds__(128) pdf_sort_kernel(const int32_t *__restrict__ ft_all,
                                                        const int32_t *__restrict__ fi_all,
-                                                       const float *__restrict__ fp_all, int S, int K, int D,
+                                                       const float *__restrict__ fp_all,
+                                                       const int32_t *__restrict__ bt_all,
+                                                       const float *__restrict__ bp_all, int S, int K, int D,
                                                        int32_t *__restrict__ pdf_ptr_all,
-                                                       uint2 *__restrict__ pdf_rec_all) {
+                                                       uint2 *__restrict__ pdf_rec_all,
+                                                       uint2 *__restrict__ bwd_rec_all,
+                                                       uint2 *__restrict__ fwd_rec_all) {
   extern __shared__ int cnt[];  // D + 1
   __shared__ int red[4];
   const int g = blockIdx.x;
@@ -65,6 +71,15 @@ __global__ void __launch_bounds__(128) pdf_sort_kernel(const int32_t *__restrict
   for (int n = tid; n <= D; n += blockDim.x) cnt[n] = 0;
   __syncthreads();
   kv = min(K, max(max(red[0], red[1]), max(red[2], red[3])));
+  {  // one 8-byte record per arc and direction (the reference layout needs three loads per arc)
+    const int32_t *bt = bt_all + (size_t)g * K * 3;
+    const float *bp = bp_all + (size_t)g * K;
+    uint2 *brec = bwd_rec_all + (size_t)g * K, *frec = fwd_rec_all + (size_t)g * K;
+    for (int k = tid; k < kv; k += blockDim.x) {
+      brec[k] = make_uint2(((unsigned)bt[3 * k] & 0xffffu) | ((unsigned)bt[3 * k + 2] << 16), __float_as_uint(bp[k]));
+      frec[k] = make_uint2(((unsigned)ft[3 * k + 1] & 0xffffu) | ((unsigned)ft[3 * k + 2] << 16), __float_as_uint(fp[k]));
+    }
+  }
   for (int k = tid; k < kv; k += blockDim.x) {
     const int pdf = ft[3 * k + 2];
     if (pdf >= 0 && pdf < D) atomicAdd(&cnt[pdf], 1);
@@ -135,6 +150,8 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
   const float *__restrict__ fin = p.fin + gb * S;
   const int32_t *__restrict__ pptr = p.pdf_ptr + gb * (D + 1);
   const uint2 *__restrict__ prec = p.pdf_rec + gb * K;
+  const uint2 *__restrict__ brec = p.bwd_rec + gb * K;
+  const uint2 *__restrict__ frec = p.fwd_rec + gb * K;
   const float *__restrict__ x = p.x + (size_t)b * T * D;
   float *__restrict__ grad = p.grad + (size_t)b * T * D;
   float *__restrict__ alpha_ws = p.alpha_ws + (size_t)b * (T + 1) * S;
@@ -180,8 +197,8 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
         float acc = 0.f;
         const int k1 = bi[2 * h + 1];
         for (int k = bi[2 * h]; k < k1; k++) {
-          const int src = bt[3 * k], pdf = bt[3 * k + 2];
-          acc += bufA[src] * bp[k] * x_s[pdf];
+          const uint2 r = __ldg(&brec[k]);
+          acc += bufA[r.x & 0xffffu] * __uint_as_float(r.y) * x_s[r.x >> 16];
         }
         const float a = acc * inv;
         bufB[h] = a;
@@ -201,14 +218,12 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
       float *aw = alpha_ws + (size_t)t * S;
       for (int h = tid; h < S; h += GEN_NT) {
         const int k0 = bi[2 * h], k1 = bi[2 * h + 1];
-        float m = -INFINITY;
-        for (int k = k0; k < k1; k++) m = fmaxf(m, bufA[bt[3 * k]] + bp[k] + x_s[bt[3 * k + 2]]);
-        float a = -INFINITY;
-        if (m > -INFINITY) {
-          float s = 0.f;
-          for (int k = k0; k < k1; k++) s += expf(bufA[bt[3 * k]] + bp[k] + x_s[bt[3 * k + 2]] - m);
-          a = m + logf(s) - tot_prev;
+        float m = -INFINITY, sm = 0.f;
+        for (int k = k0; k < k1; k++) {
+          const uint2 r = __ldg(&brec[k]);
+          lse_add(m, sm, bufA[r.x & 0xffffu] + __uint_as_float(r.y) + x_s[r.x >> 16]);
         }
+        const float a = (m > -INFINITY) ? m + logf(sm) - tot_prev : -INFINITY;
         bufB[h] = a;
         aw[h] = a;
         lse_merge(m_loc, s_loc, a, (a > -INFINITY) ? 1.f : 0.f);
@@ -275,7 +290,10 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
       for (int h = tid; h < S; h += GEN_NT) {
         float acc = 0.f;
         const int k1 = fi[2 * h + 1];
-        for (int k = fi[2 * h]; k < k1; k++) acc += fp[k] * bufB[ft[3 * k + 1]] * x_s[ft[3 * k + 2]];
+        for (int k = fi[2 * h]; k < k1; k++) {
+          const uint2 r = __ldg(&frec[k]);
+          acc += __uint_as_float(r.y) * bufB[r.x & 0xffffu] * x_s[r.x >> 16];
+        }
         const float bd = acc * inv;
         bufC[h] = bd;
         local += bd * lk[h];
@@ -294,19 +312,14 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
       for (int n = tid; n < D; n += GEN_NT) {
         const int j0 = pptr[n], j1 = pptr[n + 1];
         const float xn = x_s[n] - tot_t;
-        float m = -INFINITY;
+        float m = -INFINITY, sm = 0.f;
         for (int j = j0; j < j1; j++) {
-          const uint2 r = prec[j];
-          m = fmaxf(m, bufA[r.x & 0xffffu] + __uint_as_float(r.y) + bufB[r.x >> 16] + xn);
+          const uint2 r = __ldg(&prec[j]);
+          lse_add(m, sm, bufA[r.x & 0xffffu] + __uint_as_float(r.y) + bufB[r.x >> 16] + xn);
         }
         float lg = -INFINITY, gam = 0.f;
         if (m > -INFINITY) {
-          float s = 0.f;
-          for (int j = j0; j < j1; j++) {
-            const uint2 r = prec[j];
-            s += expf(bufA[r.x & 0xffffu] + __uint_as_float(r.y) + bufB[r.x >> 16] + xn - m);
-          }
-          lg = m + logf(s);
+          lg = m + logf(sm);
           gam = expf(lg);
         }
         gr[n] = (p.flags & CHAIN_B200_GRAD_AS_LOG) ? lg : gam;
@@ -314,14 +327,12 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
       }
       for (int h = tid; h < S; h += GEN_NT) {
         const int k0 = fi[2 * h], k1 = fi[2 * h + 1];
-        float m = -INFINITY;
-        for (int k = k0; k < k1; k++) m = fmaxf(m, fp[k] + bufB[ft[3 * k + 1]] + x_s[ft[3 * k + 2]] - tot_t);
-        float v = -INFINITY;
-        if (m > -INFINITY) {
-          float s = 0.f;
-          for (int k = k0; k < k1; k++) s += expf(fp[k] + bufB[ft[3 * k + 1]] + x_s[ft[3 * k + 2]] - tot_t - m);
-          v = m + logf(s);
+        float m = -INFINITY, sm = 0.f;
+        for (int k = k0; k < k1; k++) {
+          const uint2 r = __ldg(&frec[k]);
+          lse_add(m, sm, __uint_as_float(r.y) + bufB[r.x & 0xffffu] + x_s[r.x >> 16] - tot_t);
         }
+        const float v = (m > -INFINITY) ? m + logf(sm) : -INFINITY;
         bufC[h] = v;
       }
       if (t == 0 && p.diag) {
@@ -383,7 +394,7 @@ void launch_finalize(const float *logp, const float *diag, int B, int check_ab, 
 
 // ---------------------------------------------------------------- host side
 struct GenericWs {
-  size_t alpha, tot, pdf_ptr, pdf_rec, logp, diag, total;
+  size_t alpha, tot, pdf_ptr, pdf_rec, bwd_rec, fwd_rec, logp, diag, total;
 };
 
 static GenericWs generic_ws_layout(int B, int T, int D, int S, int K, unsigned flags) {
@@ -394,6 +405,8 @@ static GenericWs generic_ws_layout(int B, int T, int D, int S, int K, unsigned f
   w.tot = off; off = align_up(off + sizeof(float) * (size_t)B * (T + 1));
   w.pdf_ptr = off; off = align_up(off + sizeof(int32_t) * Bg * (D + 1));
   w.pdf_rec = off; off = align_up(off + sizeof(uint2) * Bg * (size_t)(K > 0 ? K : 1));
+  w.bwd_rec = off; off = align_up(off + sizeof(uint2) * Bg * (size_t)(K > 0 ? K : 1));
+  w.fwd_rec = off; off = align_up(off + sizeof(uint2) * Bg * (size_t)(K > 0 ? K : 1));
   w.logp = off; off = align_up(off + sizeof(float) * (size_t)B);
   w.diag = off; off = align_up(off + sizeof(float) * 2 * (size_t)B);
   w.total = off;
@@ -430,8 +443,9 @@ static int run_generic(const int32_t *ft, const int32_t *fi, const float *fp, co
     e = cudaFuncSetAttribute(pdf_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
     if (e != cudaSuccess) return (int)e;
   }
-  pdf_sort_kernel<<<Bg, 128, sort_smem, stream>>>(ft, fi, fp, S, K, D, (int32_t *)(base + w.pdf_ptr),
-                                                 (uint2 *)(base + w.pdf_rec));
+  pdf_sort_kernel<<<Bg, 128, sort_smem, stream>>>(ft, fi, fp, bt, bp, S, K, D, (int32_t *)(base + w.pdf_ptr),
+                                                 (uint2 *)(base + w.pdf_rec), (uint2 *)(base + w.bwd_rec),
+                                                 (uint2 *)(base + w.fwd_rec));
   g_launch_count++;
 
   GenericParams p;
@@ -445,6 +459,8 @@ static int run_generic(const int32_t *ft, const int32_t *fi, const float *fp, co
   p.tot_ws = (float *)(base + w.tot);
   p.pdf_ptr = (const int32_t *)(base + w.pdf_ptr);
   p.pdf_rec = (const uint2 *)(base + w.pdf_rec);
+  p.bwd_rec = (const uint2 *)(base + w.bwd_rec);
+  p.fwd_rec = (const uint2 *)(base + w.fwd_rec);
 
   const int nt = (S <= 160) ? 128 : (S <= 448 ? 256 : 1024);
   void (*kern)(const GenericParams) = chain_generic_kernel<LOG, 256>;
