@@ -247,7 +247,7 @@ def main():
         crit = ChainLoss(graph, 1e-5, avg=False)
         kernel_name = "den_shared_kernel + chain_generic_kernel<log>"
     else:
-        kernel_name = "chain_generic_kernel<log>" if mode == "logden" else "den_shared_kernel"
+        kernel_name = "den_shared_log_kernel" if mode == "logden" else "den_shared_kernel"
 
     class _R(object):
         pass

@@ -66,6 +66,8 @@ extern "C" {
 #define CHAIN_B200_CLAMP_X        4u  /* apply clamp(x,-30,30) (loss.py:30) inside the kernel (x is raw nnet output) */
 #define CHAIN_B200_GRAD_AS_LOG    8u  /* log domain: write log-posteriors (-inf where empty) like the reference;
                                          otherwise write posteriors, i.e. the caller's `.exp()` (loss.py:77) is fused */
+#define CHAIN_B200_LOG_DOMAIN    16u  /* chain_b200_den_prepare*: the graph is a log-domain graph (weights, init, final
+                                         are log-probabilities, no leaky HMM; S, D <= 32767) */
 
 int chain_b200_version(void);
 const char *chain_b200_status_string(int status);
@@ -105,7 +107,12 @@ int chain_b200_forward_backward_log_domain(
 
 /* ---- shared denominator graph: pack once, run many times -------------------
  * chain_b200_den_prepare_bytes: size of the packed blob for this graph (host CSR
- *   arrays in the layout above with Bg = 1), or < 0 on error.
+ *   arrays in the layout above with Bg = 1), or < 0 on error.  flags: 0 for a
+ *   probability-domain graph with leaky HMM, CHAIN_B200_LOG_DOMAIN for a log-domain
+ *   graph (leaky_host may be NULL); the same flags must be given to _prepare.
+ *   A log-domain blob makes chain_b200_den_forward_backward compute what
+ *   chain_b200_forward_backward_log_domain computes (leaky_coeff ignored,
+ *   CHAIN_B200_GRAD_AS_LOG honoured).
  * chain_b200_den_prepare: fill `blob_host` (position independent; the caller
  *   uploads it verbatim to the device, 256-byte aligned).
  * chain_b200_den_workspace_bytes: device workspace for a batch of B x T.
@@ -118,13 +125,13 @@ int chain_b200_forward_backward_log_domain(
 int64_t chain_b200_den_prepare_bytes(
     const int32_t *fwd_trans_host, const int32_t *fwd_idx_host,
     const int32_t *bwd_trans_host, const int32_t *bwd_idx_host,
-    int S, int K, int D);
+    int S, int K, int D, unsigned flags);
 
 int chain_b200_den_prepare(
     const int32_t *fwd_trans_host, const int32_t *fwd_idx_host, const float *fwd_probs_host,
     const int32_t *bwd_trans_host, const int32_t *bwd_idx_host, const float *bwd_probs_host,
     const float *leaky_host, const float *init_host, const float *final_host,
-    int S, int K, int D, void *blob_host, int64_t blob_bytes);
+    int S, int K, int D, unsigned flags, void *blob_host, int64_t blob_bytes);
 
 size_t chain_b200_den_workspace_bytes(const void *blob_host, int B, int T);
 

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("CHAIN_B200_LIB") or os.path.join(_PKG, "lib", "libcha
 c_int, c_uint, c_float, c_size_t, c_void_p, c_int64 = (
     ctypes.c_int, ctypes.c_uint, ctypes.c_float, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int64)
 
-GRAPH_SHARED, X_IS_EXP, CLAMP_X, GRAD_AS_LOG = 1, 2, 4, 8
+GRAPH_SHARED, X_IS_EXP, CLAMP_X, GRAD_AS_LOG, LOG_DOMAIN = 1, 2, 4, 8, 16
 OK, ERR_INVALID_ARG, ERR_WORKSPACE, ERR_UNSUPPORTED, ERR_BAD_BLOB = 0, -1, -2, -3, -4
 
 # every symbol include/chain_b200.h declares: name -> (restype, argtypes)
@@ -26,8 +26,8 @@ SIGNATURES = {
         c_int, [c_void_p] * 11 + [c_int] * 5 + [c_float, c_uint] + [c_void_p] * 5 + [c_void_p, c_size_t, c_int, c_void_p]),
     "chain_b200_forward_backward_log_domain": (
         c_int, [c_void_p] * 10 + [c_int] * 5 + [c_uint] + [c_void_p] * 5 + [c_void_p, c_size_t, c_int, c_void_p]),
-    "chain_b200_den_prepare_bytes": (c_int64, [c_void_p] * 4 + [c_int] * 3),
-    "chain_b200_den_prepare": (c_int, [c_void_p] * 9 + [c_int] * 3 + [c_void_p, c_int64]),
+    "chain_b200_den_prepare_bytes": (c_int64, [c_void_p] * 4 + [c_int] * 3 + [c_uint]),
+    "chain_b200_den_prepare": (c_int, [c_void_p] * 9 + [c_int] * 3 + [c_uint, c_void_p, c_int64]),
     "chain_b200_den_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "chain_b200_den_forward_backward": (
         c_int, [c_void_p] * 2 + [c_int] + [c_void_p] * 2 + [c_int] * 3 + [c_float, c_uint] + [c_void_p] * 5 +

@@ -17,6 +17,8 @@
 // control flow, no bounds checks (each stream is padded to a multiple of kFifoPairs pairs
 // plus kFifoPairs run-out pairs).  The row each lane owns in each slice comes from a
 // parallel per-warp stream of row codes, read one slice ahead.
+// Log-domain blobs (header.log_domain = 1; weights are log-probabilities, idle records carry -inf) keep
+// the end-of-slice flag in bit 31 of the index word instead (so S, D <= 32767) and are never split.
 // Rows whose degree exceeds the view's cap are split into sub-rows; a sub-row writes its
 // partial sum to a scratch slot and the listed owner adds the slots up in order.
 #pragma once
@@ -25,7 +27,7 @@
 namespace chainb200 {
 
 constexpr uint32_t kBlobMagic = 0x42324348u;  // "HC2B"
-constexpr uint32_t kBlobVersion = 6;
+constexpr uint32_t kBlobVersion = 7;
 #ifndef CHAIN_B200_NW
 #define CHAIN_B200_NW 16
 #endif
@@ -48,7 +50,7 @@ struct BlobView {
 
 struct BlobHeader {
   uint32_t magic, version;
-  int32_t S, K, D, nwarps, S_pad, D_pad, max_sub, reserved;
+  int32_t S, K, D, nwarps, S_pad, D_pad, max_sub, log_domain;
   BlobView view[3];
   int64_t off_leaky, off_init, off_final;
   int64_t total_bytes;

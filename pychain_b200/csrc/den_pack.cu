@@ -219,7 +219,7 @@ static void arrange_slice(const std::vector<const Unit *> &lanes, int width, std
 }
 
 static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, const std::vector<uint32_t> &ab,
-                       const float *w, int n_a, int n_b, bool structure_only, ViewBuild &v) {
+                       const float *w, int n_a, int n_b, bool structure_only, bool log_domain, ViewBuild &v) {
   v.n_rows = n_rows;
   const int effort = pack_effort(K);
   Rng rng(0xC0FFEEull + (uint64_t)n_rows * 7919u + (uint64_t)K);
@@ -234,6 +234,7 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
   const double mean = (double)K / std::max(1, n_rows);
   int cap = std::max(32, 4 * (int)(mean + 0.999));
   cap += cap & 1;
+  if (log_domain) cap = 1 << 30;  // log-domain rows are never split
   std::vector<Unit> units;
   units.reserve(n_rows + 64);
   v.split.clear();
@@ -288,13 +289,13 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
     width = (int)(cols.size() / 32);
     v.width[s] = width;
     s_ab[s].assign((size_t)width * 32, 0u);
-    s_w[s].assign((size_t)width * 32, 0.f);
+    s_w[s].assign((size_t)width * 32, log_domain ? -INFINITY : 0.f);
     for (int k = 0; k < width; k++) {
       uint32_t ia[32], ib[32];
       for (int l = 0; l < 32; l++) {
         const int j = cols[(size_t)k * 32 + l];
         uint32_t rec;
-        float wt = 0.f;
+        float wt = log_domain ? -INFINITY : 0.f;
         if (j >= 0) {
           rec = lanes[l]->arcs[j].ab;
           wt = lanes[l]->arcs[j].w;
@@ -352,18 +353,24 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
       rows_seq.insert(rows_seq.end(), v.rows.begin() + (size_t)s * 32, v.rows.begin() + (size_t)s * 32 + 32);
       v.rec_ab.insert(v.rec_ab.end(), s_ab[s].begin(), s_ab[s].end());
       v.rec_w.insert(v.rec_w.end(), s_w[s].begin(), s_w[s].end());
-      // end-of-slice flag: sign bit of the weight of the last record of every lane
+      // end-of-slice flag on the last record of every lane: sign bit of the weight (probabilities
+      // are >= 0), or bit 31 of the index word for log-domain blobs
       const size_t last = v.rec_w.size() - 32;
-      for (int l = 0; l < 32; l++) v.rec_w[last + l] = -fabsf(v.rec_w[last + l]) - 0.0f;
-      for (int l = 0; l < 32; l++)
-        if (!std::signbit(v.rec_w[last + l])) v.rec_w[last + l] = -0.0f;
+      for (int l = 0; l < 32; l++) {
+        if (log_domain) {
+          v.rec_ab[last + l] |= 0x80000000u;
+        } else {
+          v.rec_w[last + l] = -fabsf(v.rec_w[last + l]);
+          if (!std::signbit(v.rec_w[last + l])) v.rec_w[last + l] = -0.0f;
+        }
+      }
     }
     rows_seq.insert(rows_seq.end(), 3 * 32, -1);  // the row prefetch runs slices ahead
     size_t pairs = (v.rec_ab.size() - rec0) / 64;
     const size_t run = pairs;  // the kernel runs the last (partial) double bank through a predicated tail
     v.warp_info[3 * wv + 1] = (int64_t)run;
     v.rec_ab.insert(v.rec_ab.end(), (size_t)3 * kFifoPairs * 64, 0u);  // register-bank run-out
-    v.rec_w.insert(v.rec_w.end(), (size_t)3 * kFifoPairs * 64, 0.f);
+    v.rec_w.insert(v.rec_w.end(), (size_t)3 * kFifoPairs * 64, log_domain ? -INFINITY : 0.f);
   }
   v.rows.swap(rows_seq);
 }
@@ -372,9 +379,10 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
 
 int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, const int32_t *bt, const int32_t *bi,
                       const float *bp, const float *leaky, const float *init, const float *fin, int S, int K, int D,
-                      void *out, int64_t out_bytes) {
+                      bool log_domain, void *out, int64_t out_bytes) {
   if (S <= 0 || K <= 0 || D <= 0 || !ft || !fi || !bt || !bi) return CHAIN_B200_ERR_INVALID_ARG;
   if (S > 65535 || D > 65535) return CHAIN_B200_ERR_UNSUPPORTED;
+  if (log_domain && (S > 32767 || D > 32767)) return CHAIN_B200_ERR_UNSUPPORTED;  // bit 31 of the index word is the flag
   // validate the CSR: contiguous coverage, indices in range, rows grouped as claimed
   int kf = 0, kb = 0;
   for (int s = 0; s < S; s++) {
@@ -391,7 +399,7 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
     for (int k = fi[2 * s]; k < fi[2 * s + 1]; k++)
       if (ft[3 * k] != s) return CHAIN_B200_ERR_INVALID_ARG;
   }
-  if (fp && bp)
+  if (fp && bp && !log_domain)
     for (int k = 0; k < Kv; k++)
       if (!(fp[k] >= 0.f) || !(bp[k] >= 0.f)) return CHAIN_B200_ERR_INVALID_ARG;  // probabilities (sign bit is a flag)
   std::vector<int32_t> row_dst(Kv), row_src(Kv), row_pdf(Kv);
@@ -407,14 +415,14 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
   }
   ViewBuild vb[3];
   const bool so = (out == nullptr);
-  build_view(S, Kv, row_dst, ab_fwd, bp, S, D, so, vb[0]);
-  build_view(S, Kv, row_src, ab_bwd, fp, S, D, so, vb[1]);
-  build_view(D, Kv, row_pdf, ab_gam, fp, S, S, so, vb[2]);
+  build_view(S, Kv, row_dst, ab_fwd, bp, S, D, so, log_domain, vb[0]);
+  build_view(S, Kv, row_src, ab_bwd, fp, S, D, so, log_domain, vb[1]);
+  build_view(D, Kv, row_pdf, ab_gam, fp, S, S, so, log_domain, vb[2]);
 
   BlobHeader h;
   memset(&h, 0, sizeof(h));
   h.magic = kBlobMagic; h.version = kBlobVersion;
-  h.S = S; h.K = Kv; h.D = D; h.nwarps = DEN_NW;
+  h.S = S; h.K = Kv; h.D = D; h.nwarps = DEN_NW; h.log_domain = log_domain ? 1 : 0;
   h.S_pad = (S + 3) / 4 * 4; h.D_pad = (D + 3) / 4 * 4;
   size_t off = align_up(sizeof(BlobHeader));
   for (int i = 0; i < 3; i++) {
@@ -435,7 +443,7 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
   h.off_final = (int64_t)off; off = align_up(off + (size_t)h.S_pad * 4);
   h.total_bytes = (int64_t)off;
   if (!out) return h.total_bytes;
-  if (out_bytes < h.total_bytes || !fp || !bp || !leaky || !init || !fin) return CHAIN_B200_ERR_INVALID_ARG;
+  if (out_bytes < h.total_bytes || !fp || !bp || (!leaky && !log_domain) || !init || !fin) return CHAIN_B200_ERR_INVALID_ARG;
   char *base = (char *)out;
   memset(base, 0, (size_t)h.total_bytes);
   memcpy(base, &h, sizeof(h));
@@ -451,7 +459,7 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
       memcpy(&rec[2 * j + 1], &b.rec_w[j], 4);
     }
   }
-  memcpy(base + h.off_leaky, leaky, (size_t)S * 4);
+  if (leaky) memcpy(base + h.off_leaky, leaky, (size_t)S * 4);
   memcpy(base + h.off_init, init, (size_t)S * 4);
   memcpy(base + h.off_final, fin, (size_t)S * 4);
   return h.total_bytes;
@@ -464,15 +472,17 @@ using namespace chainb200;
 extern "C" {
 
 int64_t chain_b200_den_prepare_bytes(const int32_t *ft, const int32_t *fi, const int32_t *bt, const int32_t *bi, int S,
-                                     int K, int D) {
-  return pack_den_blob(ft, fi, nullptr, bt, bi, nullptr, nullptr, nullptr, nullptr, S, K, D, nullptr, 0);
+                                     int K, int D, unsigned flags) {
+  return pack_den_blob(ft, fi, nullptr, bt, bi, nullptr, nullptr, nullptr, nullptr, S, K, D,
+                       (flags & CHAIN_B200_LOG_DOMAIN) != 0, nullptr, 0);
 }
 
 int chain_b200_den_prepare(const int32_t *ft, const int32_t *fi, const float *fp, const int32_t *bt,
                            const int32_t *bi, const float *bp, const float *leaky, const float *init,
-                           const float *fin, int S, int K, int D, void *blob, int64_t blob_bytes) {
+                           const float *fin, int S, int K, int D, unsigned flags, void *blob, int64_t blob_bytes) {
   if (!blob) return CHAIN_B200_ERR_INVALID_ARG;
-  const int64_t r = pack_den_blob(ft, fi, fp, bt, bi, bp, leaky, init, fin, S, K, D, blob, blob_bytes);
+  const int64_t r = pack_den_blob(ft, fi, fp, bt, bi, bp, leaky, init, fin, S, K, D,
+                                  (flags & CHAIN_B200_LOG_DOMAIN) != 0, blob, blob_bytes);
   return r < 0 ? (int)r : CHAIN_B200_OK;
 }
 

@@ -24,102 +24,9 @@
 //    exp/clamp are applied while transposing them into the interleaved layout.
 //  * leaky-HMM mixing, per-frame renormalisation, total log-likelihood, the t=0 self-check
 //    and the zeroing of padded frames are all inside the one kernel.
-#include <algorithm>
-#include <cstdlib>
-
-#include "common.cuh"
-#include "den_blob.h"
+#include "den_kernel_common.cuh"
 
 namespace chainb200 {
-
-// ------------------------------------------------------------------------------- device
-struct DView {
-  const int64_t *warp_info;  // [DEN_NW][3] {stream offset, pairs to run, row-code offset}
-  const int32_t *rows, *split;
-  const uint2 *recs;
-  int n_split;
-};
-
-struct DenParams {
-  DView view[3];
-  const float *leaky, *init, *fin;
-  const float *x;
-  const int64_t *lengths;
-  int B, T, D, S, S_pad, D_pad;
-  float coeff;
-  unsigned flags;
-  float *logp, *grad, *diag;
-  float *alpha_ws, *tot_ws;
-  int num_groups, use_tma_x;
-  int n_rep;           // copies of the blob laid out back to back on the device
-  size_t rep_stride;   // bytes between copies
-};
-
-template <int G> struct Vec;
-template <> struct Vec<4> { using type = float4; };
-template <> struct Vec<2> { using type = float2; };
-template <> struct Vec<1> { using type = float; };
-
-template <int G> __device__ __forceinline__ void ld_vec(const float *p, float (&v)[G]);
-template <> __device__ __forceinline__ void ld_vec<4>(const float *p, float (&v)[4]) {
-  const float4 t = *reinterpret_cast<const float4 *>(p);
-  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-}
-template <> __device__ __forceinline__ void ld_vec<2>(const float *p, float (&v)[2]) {
-  const float2 t = *reinterpret_cast<const float2 *>(p);
-  v[0] = t.x; v[1] = t.y;
-}
-template <> __device__ __forceinline__ void ld_vec<1>(const float *p, float (&v)[1]) { v[0] = *p; }
-
-template <int G> __device__ __forceinline__ void st_vec(float *p, const float (&v)[G]);
-template <> __device__ __forceinline__ void st_vec<4>(float *p, const float (&v)[4]) {
-  *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
-}
-template <> __device__ __forceinline__ void st_vec<2>(float *p, const float (&v)[2]) {
-  *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
-}
-template <> __device__ __forceinline__ void st_vec<1>(float *p, const float (&v)[1]) { *p = v[0]; }
-
-__device__ __forceinline__ uint2 ldg_stream(const uint2 *p) {
-  uint2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-  return r;
-}
-// Refill a FIFO slot IN PLACE: the "+r" operands make the load depend on the slot's previous
-// contents, so the compiler can neither hoist it above the consumers of the old pair nor
-// stage it through a temporary (a copy out of a temporary would wait for the load).
-__device__ __forceinline__ void ldg_stream_into(uint2 &r, const uint2 *p) {
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "+r"(r.x), "+r"(r.y) : "l"(p));
-}
-__device__ __forceinline__ void ldg_into(int &r, const int32_t *p) {
-  asm volatile("ld.global.nc.u32 %0, [%1];" : "+r"(r) : "l"(p));
-}
-
-// ---- mbarrier / TMA bulk helpers (cp.async.bulk: SASS UBLKCP) ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int G>
 __device__ __forceinline__ void consume_rec(const uint32_t ab, const float w, const float *__restrict__ A,
@@ -226,25 +133,6 @@ __device__ __forceinline__ void fixup_split(const DView &v, const float *__restr
     }
     epi(row, acc);
   }
-}
-
-// sum over the block of G per-thread values; result to every thread.
-template <int G>
-__device__ __forceinline__ void block_sum_vec(float (&v)[G], float *red /* [DEN_NW*G] */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int g = 0; g < G; g++) {
-    v[g] = warp_sum(v[g]);
-    if (lane == 0) red[warp * G + g] = v[g];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int g = 0; g < G; g++) {
-    float t = 0.f;
-    for (int w = 0; w < DEN_NW; w++) t += red[w * G + g];
-    v[g] = t;
-  }
-  __syncthreads();
 }
 
 template <int G>
@@ -575,47 +463,6 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
 }
 
 
-struct DenWs {
-  size_t alpha, tot, logp, diag, total;
-};
-static DenWs den_ws_layout(const BlobHeader &h, int B, int T) {
-  DenWs w;
-  size_t off = 0;
-  const size_t Bp = (size_t)B + 3;
-  w.alpha = off; off = align_up(off + sizeof(float) * Bp * (T + 1) * h.S_pad);
-  w.tot = off; off = align_up(off + sizeof(float) * Bp * (T + 1));
-  w.logp = off; off = align_up(off + sizeof(float) * Bp);
-  w.diag = off; off = align_up(off + sizeof(float) * 2 * Bp);
-  w.total = off;
-  return w;
-}
-
-static size_t den_smem_bytes(const BlobHeader &h, int G) {
-  return sizeof(float) * ((size_t)2 * h.S_pad * G + (size_t)3 * h.D_pad * G + (size_t)h.max_sub * G) + 128;
-}
-
-// Relative cost of one frame for a group of G utterances (shared-memory wavefronts of
-// the vector gathers), used to pick G: time ~ waves(G) * cost(G).
-static int choose_G(const BlobHeader &h, int B, int num_sms) {
-  const char *env = getenv("CHAIN_B200_G");
-  if (env) {
-    const int g = atoi(env);
-    if ((g == 1 || g == 2 || g == 4) && den_smem_bytes(h, g) <= 227 * 1024) return g;
-  }
-  // measured on B200 (cfg4): a frame of a G-group costs nearly the same for every G (the gathers are
-  // wavefront-bound, not byte-bound), so minimise the number of rounds first, then prefer the smaller G
-  const double cost[5] = {0, 0.84, 0.88, 0, 1.0};
-  int best = 0;
-  double best_t = 1e30;
-  for (int g : {4, 2, 1}) {
-    if (den_smem_bytes(h, g) > 227 * 1024) continue;
-    const int groups = (B + g - 1) / g;
-    const double t = (double)((groups + num_sms - 1) / num_sms) * cost[g];
-    if (t < best_t - 1e-9) { best_t = t; best = g; }
-  }
-  return best;
-}
-
 }  // namespace chainb200
 
 using namespace chainb200;
@@ -638,7 +485,7 @@ int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev,
   if (hp->magic != kBlobMagic || hp->version != kBlobVersion || hp->nwarps != DEN_NW) return CHAIN_B200_ERR_BAD_BLOB;
   const BlobHeader h = *hp;
   if (B <= 0 || T <= 0 || D != h.D || !x || !lengths || !objf || !grad || !ok) return CHAIN_B200_ERR_INVALID_ARG;
-  if (!(coeff > 0.f && coeff < 1.f)) return CHAIN_B200_ERR_INVALID_ARG;  // chain-computation.cc:68
+  if (!h.log_domain && !(coeff > 0.f && coeff < 1.f)) return CHAIN_B200_ERR_INVALID_ARG;  // chain-computation.cc:68
   const DenWs w = den_ws_layout(h, B, T);
   if (!ws || ws_bytes < w.total) return CHAIN_B200_ERR_WORKSPACE;
 
@@ -680,6 +527,14 @@ int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev,
 
   const int grid = std::min(p.num_groups, num_sms);
   cudaError_t e;
+  if (h.log_domain) {  // same blob layout, log semiring (den_shared_log.cu)
+    const int st = launch_den_shared_log(h, p, G, grid, smem, stream);
+    if (st != 0) return st;
+    g_launch_count++;
+    launch_finalize(p.logp, p.diag, B, 0, objf, ok, diag, stream);
+    g_launch_count++;
+    return (int)cudaGetLastError();
+  }
 #define LAUNCH_DEN(GG)                                                                                          \
   do {                                                                                                          \
     e = cudaFuncSetAttribute(den_shared_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \

@@ -151,26 +151,33 @@ class PreparedDenGraph(object):
 _prepared_cache = OrderedDict()
 
 
-def prepare_den_graph(graph_tensors, num_states, D, device):
-    """Pack (once; cached) a single prob-domain graph given its reference-layout
-    tensors (row 0 of each is used).  `graph_tensors` order = _GRAPH_NAMES_PROB."""
+def prepare_den_graph(graph_tensors, num_states, D, device, log_domain=False):
+    """Pack (once; cached) a single graph given its reference-layout tensors (row 0 of each is
+    used).  `graph_tensors` order = _GRAPH_NAMES_PROB, or _GRAPH_NAMES_LOG for a log-domain graph."""
     lib = _cabi.lib()
+    names = _GRAPH_NAMES_LOG if log_domain else _GRAPH_NAMES_PROB
     rows = [t[0] if t.dim() == (3 if "transition" in n and "probs" not in n else 2) else t
-            for t, n in zip(graph_tensors, _GRAPH_NAMES_PROB)]
-    key = (tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in rows), int(D), str(device))
+            for t, n in zip(graph_tensors, names)]
+    key = (tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in rows), int(D), str(device), bool(log_domain))
     hit = _prepared_cache.get(key)
     if hit is not None:
         _prepared_cache.move_to_end(key)
         return hit[1]
     host = [t.detach().cpu().contiguous() for t in rows]
-    ft, fi, fp, bt, bi, bp, lk, ini, fin = host
+    if log_domain:
+        ft, fi, fp, bt, bi, bp, ini, fin = host
+        lk = None
+    else:
+        ft, fi, fp, bt, bi, bp, lk, ini, fin = host
     S, K = int(num_states), int(ft.size(0))
-    nbytes = lib.chain_b200_den_prepare_bytes(_ptr(ft), _ptr(fi), _ptr(bt), _ptr(bi), S, K, int(D))
+    pflags = _cabi.LOG_DOMAIN if log_domain else 0
+    nbytes = lib.chain_b200_den_prepare_bytes(_ptr(ft), _ptr(fi), _ptr(bt), _ptr(bi), S, K, int(D), pflags)
     if nbytes < 0:
         _cabi.check(int(nbytes), "chain_b200_den_prepare_bytes")
     blob = torch.empty(int(nbytes), dtype=torch.uint8).pin_memory() if torch.cuda.is_available() else \
         torch.empty(int(nbytes), dtype=torch.uint8)
-    st = lib.chain_b200_den_prepare(*[_ptr(t) for t in host], S, K, int(D), _ptr(blob), int(nbytes))
+    st = lib.chain_b200_den_prepare(_ptr(ft), _ptr(fi), _ptr(fp), _ptr(bt), _ptr(bi), _ptr(bp), _ptr(lk), _ptr(ini),
+                                    _ptr(fin), S, K, int(D), pflags, _ptr(blob), int(nbytes))
     _cabi.check(st, "chain_b200_den_prepare")
     copies = int(os.environ.get("CHAIN_B200_BLOB_COPIES", "1"))
     blob_dev = blob.to(device).repeat(copies) if torch.device(device).type == "cuda" else None
@@ -223,7 +230,15 @@ def forward_backward_prob(graph_tensors, x, lengths, num_states, leaky_coefficie
     return _run_generic(False, graph_tensors, x, lengths, num_states, leaky_coefficient, flags)
 
 
-def forward_backward_log(graph_tensors, x, lengths, num_states, grad_as_log=True, clamp=False):
-    """Log-domain (numerator) forward-backward.  `graph_tensors` in _GRAPH_NAMES_LOG order."""
+def forward_backward_log(graph_tensors, x, lengths, num_states, grad_as_log=True, clamp=False, path=None):
+    """Log-domain (numerator) forward-backward.  `graph_tensors` in _GRAPH_NAMES_LOG order.
+    A graph shared by the whole batch (stride-0 views) with >= 256 arcs runs on the packed
+    shared-graph kernels, per-utterance graphs on the general kernel."""
     flags = (GRAD_AS_LOG if grad_as_log else 0) | (CLAMP_X if clamp else 0)
+    path = path or DEN_PATH
+    S, K = int(num_states), int(graph_tensors[0].size(1))
+    if (path != "generic" and x.size(0) > 1 and _is_shared(graph_tensors, x.size(0)) and K >= 256
+            and S <= 32767 and x.size(2) <= 32767):
+        prep = prepare_den_graph(graph_tensors, num_states, x.size(2), x.device, log_domain=True)
+        return _run_den_shared(prep, x, lengths, 0.5, flags)
     return _run_generic(True, graph_tensors, x, lengths, num_states, 0.0, flags)

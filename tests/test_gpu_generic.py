@@ -91,20 +91,40 @@ def test_num_generic_vs_oracle(cuda, B, T, D, variable):
         assert (rows[b, :int(lengths[b])] - 1).abs().max().item() < 1e-4
 
 
-def test_log_domain_shared_graph(cuda):
-    """BASELINE cfg2 flavour: a (leaky-free) denominator graph run through the
-    log-domain entry, shared by the batch."""
-    fst = synth.random_den_fst(60, 400, 24, seed=1002)
+@pytest.mark.parametrize("path", ["generic", "G1", "G2", "G4"])
+def test_log_domain_shared_graph(cuda, path):
+    """BASELINE cfg2 flavour: a (leaky-free) denominator graph run through the log-domain entry,
+    shared by the batch: the general kernel and the packed shared-graph log kernel (every G)."""
+    import os
+    fst = synth.random_den_fst(61, 400, 23, seed=1002)   # D % 4 != 0, S % 4 != 0
     g = ChainGraph(fst, log_domain=True)
-    B, T, D = 4, 40, 24
+    B, T, D = 7, 40, 23
     gb = ChainGraphBatch(g, B)
     x, lengths = synth.make_inputs(B, T, D, seed=9, variable=True)
-    x = x.clamp(-30, 30)
-    o_c, _, lg_c, _, _ = co.num_c(gb, x, lengths)
+    lengths[-1] = 0
+    x = x * 5.0
+    o_c, lp_c, lg_c, ok_c, _ = co.num_c(gb, x.clamp(-30, 30), lengths)
     gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_LOG)
-    r = engine.forward_backward_log(gt, x.to(cuda), lengths, gb.num_states, grad_as_log=True)
+    if path != "generic":
+        os.environ["CHAIN_B200_G"] = path[1]
+    try:
+        r = engine.forward_backward_log(gt, x.to(cuda), lengths, gb.num_states, grad_as_log=True, clamp=True,
+                                        path="generic" if path == "generic" else "auto")
+        r2 = engine.forward_backward_log(gt, x.to(cuda), lengths, gb.num_states, grad_as_log=False, clamp=True,
+                                         path="generic" if path == "generic" else "auto")
+    finally:
+        os.environ.pop("CHAIN_B200_G", None)
     assert rel(r.objf.item(), o_c) < OBJF_RTOL
+    assert (r.logp.cpu() - lp_c).abs().max() < 1e-4 * max(1.0, lp_c.abs().max().item())
     assert (r.grad.cpu().exp() - lg_c.exp()).abs().max().item() < GRAD_ATOL
+    assert (r2.grad.cpu() - lg_c.exp()).abs().max().item() < GRAD_ATOL
+    m = lg_c > -20
+    assert (r.grad.cpu()[m] - lg_c[m]).abs().max().item() < 1e-3
+    for b in range(B):
+        L = int(lengths[b])
+        if L < T:
+            assert torch.isneginf(r.grad[b, L:]).all() and r2.grad[b, L:].abs().max().item() == 0
+    assert int(r.ok.item()) == 1
 
 
 @pytest.mark.skipif(not co.ref_available(), reason="prebuilt reference extension (oracle/_ref) not present")

@@ -36,11 +36,18 @@ def test_den_kernels_match_reference_golden(cuda, name, path):
 
 
 @pytest.mark.parametrize("name", sorted(mg.NUM_CASES) + sorted(mg.LOGDEN_CASES))
-def test_log_domain_kernel_matches_reference_golden(cuda, name):
+@pytest.mark.parametrize("path", ["generic", "G1", "G4"])
+def test_log_domain_kernel_matches_reference_golden(cuda, name, path):
     gold = load(name)
     graphs, x, lengths = mg.num_inputs(mg.NUM_CASES[name]) if name in mg.NUM_CASES else mg.logden_inputs(mg.LOGDEN_CASES[name])
     gt = tuple(getattr(graphs, n) for n in engine._GRAPH_NAMES_LOG)
-    r = engine.forward_backward_log(gt, x.to(cuda), lengths, graphs.num_states, grad_as_log=True)
+    if path != "generic":
+        os.environ["CHAIN_B200_G"] = path[1]
+    try:
+        r = engine.forward_backward_log(gt, x.to(cuda), lengths, graphs.num_states, grad_as_log=True,
+                                        path="generic" if path == "generic" else "auto")
+    finally:
+        os.environ.pop("CHAIN_B200_G", None)
     assert rel(r.objf.item(), gold["objf"]) < 2e-6
     lg = r.grad.cpu().numpy()
     assert np.abs(np.exp(lg) - np.exp(gold["log_grad"])).max() < 2e-5

@@ -231,9 +231,10 @@ def test_den_packer_rejects_bad_graphs():
     ft, fi, bt, bi = (g.forward_transitions.clone(), g.forward_transition_indices.clone(),
                       g.backward_transitions.clone(), g.backward_transition_indices.clone())
     p = lambda t: ctypes.c_void_p(t.data_ptr())
-    assert lib.chain_b200_den_prepare_bytes(p(ft), p(fi), p(bt), p(bi), 10, 30, 8) > 0
-    assert lib.chain_b200_den_prepare_bytes(p(ft), p(fi), p(bt), p(bi), 10, 30, 4) == _cabi.ERR_INVALID_ARG  # pdf out of range
+    assert lib.chain_b200_den_prepare_bytes(p(ft), p(fi), p(bt), p(bi), 10, 30, 8, 0) > 0
+    assert lib.chain_b200_den_prepare_bytes(p(ft), p(fi), p(bt), p(bi), 10, 30, 4, 0) == _cabi.ERR_INVALID_ARG  # pdf out of range
     bad = ft.clone(); bad[3, 1] = 99
-    assert lib.chain_b200_den_prepare_bytes(p(bad), p(fi), p(bt), p(bi), 10, 30, 8) == _cabi.ERR_INVALID_ARG
-    assert lib.chain_b200_den_prepare_bytes(p(ft), p(fi), p(bt), p(bi), 70000, 30, 8) == _cabi.ERR_UNSUPPORTED
+    assert lib.chain_b200_den_prepare_bytes(p(bad), p(fi), p(bt), p(bi), 10, 30, 8, 0) == _cabi.ERR_INVALID_ARG
+    assert lib.chain_b200_den_prepare_bytes(p(ft), p(fi), p(bt), p(bi), 70000, 30, 8, 0) == _cabi.ERR_UNSUPPORTED
+    assert lib.chain_b200_den_prepare_bytes(p(ft), p(fi), p(bt), p(bi), 40000, 30, 8, _cabi.LOG_DOMAIN) == _cabi.ERR_UNSUPPORTED
     assert lib.chain_b200_den_workspace_bytes(p(torch.zeros(512, dtype=torch.uint8)), 4, 10) == 0  # not a blob

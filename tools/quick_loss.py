@@ -21,7 +21,7 @@ x, lengths = synth.make_inputs(c["B"], c["T"], c["D"], seed=2002)
 xd = x.cuda()
 gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_LOG)
 ms = timeit(lambda: engine.forward_backward_log(gt, xd, lengths, gb.num_states, grad_as_log=False, clamp=True))
-print(f"cfg2 log-domain den (generic kernel): {ms:.3f} ms  {c['B']*c['T']/ms/1e3:.2f} Mframes/s")
+print(f"cfg2 log-domain den (shared-graph log kernel): {ms:.3f} ms  {c['B']*c['T']/ms/1e3:.2f} Mframes/s")
 
 # cfg3: full ChainLoss, variable T
 c = synth.CONFIGS["cfg3"]
@@ -43,3 +43,9 @@ ms_n = timeit(lambda: engine.forward_backward_log(gtn, xc, lengths, nb.num_state
 gbd = ChainGraphBatch(den, c["B"]); gtd = tuple(getattr(gbd, n) for n in engine._GRAPH_NAMES_PROB)
 ms_d = timeit(lambda: engine.forward_backward_prob(gtd, xc, lengths, gbd.num_states, 1e-5, x_is_exp=False, clamp=True))
 print(f"   numerator alone {ms_n:.3f} ms, denominator alone {ms_d:.3f} ms")
+ChainLoss.overlap_streams = False
+ms2 = timeit(step)
+print(f"   ChainLoss without stream overlap: {ms2:.3f} ms")
+ChainLoss.overlap_streams = True
+ms3 = timeit(step)
+print(f"   ChainLoss with stream overlap again: {ms3:.3f} ms")
