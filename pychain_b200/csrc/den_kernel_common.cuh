@@ -56,19 +56,12 @@ template <> __device__ __forceinline__ void st_vec<2>(float *p, const float (&v)
 }
 template <> __device__ __forceinline__ void st_vec<1>(float *p, const float (&v)[1]) { *p = v[0]; }
 
+template <bool L1C>
 __device__ __forceinline__ uint2 ldg_stream(const uint2 *p) {
   uint2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  if (L1C) asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  else asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
-}
-// Refill a FIFO slot IN PLACE: the "+r" operands make the load depend on the slot's previous
-// contents, so the compiler can neither hoist it above the consumers of the old pair nor
-// stage it through a temporary (a copy out of a temporary would wait for the load).
-__device__ __forceinline__ void ldg_stream_into(uint2 &r, const uint2 *p) {
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "+r"(r.x), "+r"(r.y) : "l"(p));
-}
-__device__ __forceinline__ void ldg_into(int &r, const int32_t *p) {
-  asm volatile("ld.global.nc.u32 %0, [%1];" : "+r"(r) : "l"(p));
 }
 
 // ---- mbarrier / TMA bulk helpers (cp.async.bulk: SASS UBLKCP) ----
@@ -159,6 +152,14 @@ inline int choose_G(const BlobHeader &h, int B, int num_sms) {
 
 
 // defined in den_shared_log.cu
-int launch_den_shared_log(const BlobHeader &h, const DenParams &p, int G, int grid, size_t smem, cudaStream_t stream);
+int launch_den_shared_log(const BlobHeader &h, const DenParams &p, int G, bool l1c, int grid, size_t smem, cudaStream_t stream);
+
+// Do the record streams of all three views fit in L1 next to the CTA's shared memory?
+inline bool records_fit_l1(const BlobHeader &h, size_t smem) {
+  // n_recs includes the (never consumed) register-bank run-out of every warp stream
+  const int64_t runout = (int64_t)DEN_NW * 3 * kFifoPairs * 64;
+  const size_t recs = (size_t)(h.view[0].n_recs + h.view[1].n_recs + h.view[2].n_recs - 3 * runout) * 8;
+  return recs + smem + 24 * 1024 <= 228 * 1024;
+}
 
 }  // namespace chainb200

@@ -46,7 +46,7 @@ __device__ __forceinline__ void consume_rec(const uint32_t ab, const float w, co
 // flight to cover the L2 latency and no load ever lands in a register that is still live.
 // The sign bit of the second weight of a pair ends a slice: run the epilogue for the lane's
 // row and move to the next row code (fetched two slices ahead).
-template <int G, class Epi>
+template <int G, bool L1C, class Epi>
 __device__ __forceinline__ void sell_pass(const DView &v, const float *__restrict__ A, const float *__restrict__ Bv,
                                           float *__restrict__ partial, int warp, int lane, Epi &epi) {
   const uint2 *sp = v.recs + v.warp_info[3 * warp] + lane;
@@ -55,8 +55,8 @@ __device__ __forceinline__ void sell_pass(const DView &v, const float *__restric
   uint2 fa[kFifoPairs][2], fb[kFifoPairs][2];
 #pragma unroll
   for (int d = 0; d < kFifoPairs; d++) {
-    fa[d][0] = ldg_stream(sp + (2 * d) * 32);
-    fa[d][1] = ldg_stream(sp + (2 * d + 1) * 32);
+    fa[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
+    fa[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
   }
   sp += 2 * kFifoPairs * 32;
   int row = __ldg(rp), row_n1 = __ldg(rp + 32), row_n2 = __ldg(rp + 64);
@@ -82,16 +82,16 @@ __device__ __forceinline__ void sell_pass(const DView &v, const float *__restric
   for (; j + 2 * kFifoPairs <= npairs; j += 2 * kFifoPairs) {  // full double banks: straight-line code
 #pragma unroll
     for (int d = 0; d < kFifoPairs; d++) {
-      fb[d][0] = ldg_stream(sp + (2 * d) * 32);
-      fb[d][1] = ldg_stream(sp + (2 * d + 1) * 32);
+      fb[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
+      fb[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
     }
     sp += 2 * kFifoPairs * 32;
 #pragma unroll
     for (int d = 0; d < kFifoPairs; d++) process(fa[d][0], fa[d][1]);
 #pragma unroll
     for (int d = 0; d < kFifoPairs; d++) {
-      fa[d][0] = ldg_stream(sp + (2 * d) * 32);
-      fa[d][1] = ldg_stream(sp + (2 * d + 1) * 32);
+      fa[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
+      fa[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
     }
     sp += 2 * kFifoPairs * 32;
 #pragma unroll
@@ -102,8 +102,8 @@ __device__ __forceinline__ void sell_pass(const DView &v, const float *__restric
     if (rem > kFifoPairs) {
 #pragma unroll
       for (int d = 0; d < kFifoPairs; d++) {
-        fb[d][0] = ldg_stream(sp + (2 * d) * 32);
-        fb[d][1] = ldg_stream(sp + (2 * d + 1) * 32);
+        fb[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
+        fb[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
       }
     }
 #pragma unroll
@@ -135,7 +135,10 @@ __device__ __forceinline__ void fixup_split(const DView &v, const float *__restr
   }
 }
 
-template <int G>
+// L1C: the three record streams fit in the L1 next to this CTA's shared memory, so they are
+// loaded with L1 allocation and hit L1 from the second frame on (small graphs are latency bound);
+// otherwise they are streamed from L2 without polluting L1.
+template <int G, bool L1C>
 __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar[2];  // 0: alpha rows, 1: x frames
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         for (int g = 0; g < G; g++) { o[g] = acc[g] * inv[g]; part[g] += o[g]; }
         st_vec<G>(Bn + (size_t)row * G, o);
       };
-      sell_pass<G>(views[0], A, x_s, partial, warp, lane, epi_fwd);
+      sell_pass<G, L1C>(views[0], A, x_s, partial, warp, lane, epi_fwd);
       if (p.view[0].n_split) { __syncthreads(); fixup_split<G>(p.view[0], partial, epi_fwd); }
 #pragma unroll
       for (int g = 0; g < G; g++) {
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         for (int g = 0; g < G; g++) { o[g] = acc[g] * xv[g] * inv[g]; gsum[g] += o[g]; }
         st_vec<G>(gam_s + (size_t)row * G, o);
       };
-      sell_pass<G>(views[2], P, Q, partial, warp, lane, epi_gam);
+      sell_pass<G, L1C>(views[2], P, Q, partial, warp, lane, epi_gam);
       if (p.view[2].n_split) { __syncthreads(); fixup_split<G>(p.view[2], partial, epi_gam); }
       __syncthreads();  // gamma rows complete; everybody done reading P
 
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         for (int g = 0; g < G; g++) { o[g] = acc[g] * inv[g]; lpart[g] = fmaf(o[g], l, lpart[g]); }
         st_vec<G>(P + (size_t)row * G, o);
       };
-      sell_pass<G>(views[1], Q, x_s, partial, warp, lane, epi_bwd);
+      sell_pass<G, L1C>(views[1], Q, x_s, partial, warp, lane, epi_bwd);
       if (p.view[1].n_split) { __syncthreads(); fixup_split<G>(p.view[1], partial, epi_bwd); }
 #pragma unroll
       for (int g = 0; g < G; g++) {
@@ -526,24 +529,31 @@ int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev,
   p.rep_stride = (size_t)h.total_bytes;
 
   const int grid = std::min(p.num_groups, num_sms);
+  const bool l1c = records_fit_l1(h, smem) && !getenv("CHAIN_B200_NO_L1_RECORDS");
   cudaError_t e;
   if (h.log_domain) {  // same blob layout, log semiring (den_shared_log.cu)
-    const int st = launch_den_shared_log(h, p, G, grid, smem, stream);
+    const int st = launch_den_shared_log(h, p, G, l1c, grid, smem, stream);
     if (st != 0) return st;
     g_launch_count++;
     launch_finalize(p.logp, p.diag, B, 0, objf, ok, diag, stream);
     g_launch_count++;
     return (int)cudaGetLastError();
   }
-#define LAUNCH_DEN(GG)                                                                                          \
-  do {                                                                                                          \
-    e = cudaFuncSetAttribute(den_shared_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    if (e != cudaSuccess) return (int)e;                                                                        \
-    den_shared_kernel<GG><<<grid, DEN_NT, smem, stream>>>(p);                                                   \
+#define LAUNCH_DEN(GG, LL)                                                                                          \
+  do {                                                                                                              \
+    e = cudaFuncSetAttribute(den_shared_kernel<GG, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e != cudaSuccess) return (int)e;                                                                            \
+    den_shared_kernel<GG, LL><<<grid, DEN_NT, smem, stream>>>(p);                                                   \
   } while (0)
-  if (G == 4) LAUNCH_DEN(4);
-  else if (G == 2) LAUNCH_DEN(2);
-  else LAUNCH_DEN(1);
+  if (l1c) {
+    if (G == 4) LAUNCH_DEN(4, true);
+    else if (G == 2) LAUNCH_DEN(2, true);
+    else LAUNCH_DEN(1, true);
+  } else {
+    if (G == 4) LAUNCH_DEN(4, false);
+    else if (G == 2) LAUNCH_DEN(2, false);
+    else LAUNCH_DEN(1, false);
+  }
 #undef LAUNCH_DEN
   g_launch_count++;
   launch_finalize(p.logp, p.diag, B, 1, objf, ok, diag, stream);

@@ -38,7 +38,7 @@ __device__ __forceinline__ void lse_rec(const uint32_t ab, const float w, const 
 // row's records into a running (max, sum-exp) per utterance.  Record streams and the
 // two-bank register prefetch are those of den_shared.cu; the end-of-slice flag is bit 31 of
 // the index word.
-template <int G, class Epi>
+template <int G, bool L1C, class Epi>
 __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__restrict__ A,
                                               const float *__restrict__ Bv, int warp, int lane, Epi &epi) {
   const uint2 *sp = v.recs + v.warp_info[3 * warp] + lane;
@@ -47,8 +47,8 @@ __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__res
   uint2 fa[kFifoPairs][2], fb[kFifoPairs][2];
 #pragma unroll
   for (int d = 0; d < kFifoPairs; d++) {
-    fa[d][0] = ldg_stream(sp + (2 * d) * 32);
-    fa[d][1] = ldg_stream(sp + (2 * d + 1) * 32);
+    fa[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
+    fa[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
   }
   sp += 2 * kFifoPairs * 32;
   int row = __ldg(rp), row_n1 = __ldg(rp + 32), row_n2 = __ldg(rp + 64);
@@ -78,16 +78,16 @@ __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__res
   for (; j + 2 * kFifoPairs <= npairs; j += 2 * kFifoPairs) {
 #pragma unroll
     for (int d = 0; d < kFifoPairs; d++) {
-      fb[d][0] = ldg_stream(sp + (2 * d) * 32);
-      fb[d][1] = ldg_stream(sp + (2 * d + 1) * 32);
+      fb[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
+      fb[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
     }
     sp += 2 * kFifoPairs * 32;
 #pragma unroll
     for (int d = 0; d < kFifoPairs; d++) process(fa[d][0], fa[d][1]);
 #pragma unroll
     for (int d = 0; d < kFifoPairs; d++) {
-      fa[d][0] = ldg_stream(sp + (2 * d) * 32);
-      fa[d][1] = ldg_stream(sp + (2 * d + 1) * 32);
+      fa[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
+      fa[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
     }
     sp += 2 * kFifoPairs * 32;
 #pragma unroll
@@ -98,8 +98,8 @@ __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__res
     if (rem > kFifoPairs) {
 #pragma unroll
       for (int d = 0; d < kFifoPairs; d++) {
-        fb[d][0] = ldg_stream(sp + (2 * d) * 32);
-        fb[d][1] = ldg_stream(sp + (2 * d + 1) * 32);
+        fb[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
+        fb[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
       }
     }
 #pragma unroll
@@ -136,7 +136,7 @@ __device__ __forceinline__ void block_lse_vec(float (&m)[G], float (&s)[G], floa
   __syncthreads();
 }
 
-template <int G>
+template <int G, bool L1C>
 __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar[2];  // 0: alpha rows, 1: x frames
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
         }
         st_vec<G>(Bn + (size_t)row * G, a);
       };
-      sell_pass_log<G>(p.view[0], A, x_s, warp, lane, epi_fwd);
+      sell_pass_log<G, L1C>(p.view[0], A, x_s, warp, lane, epi_fwd);
       float nsc[G];
       block_lse_vec<G>(pm, ps, nsc, red);  // contains the barrier that publishes alpha(t)
       float *awt = aws + (size_t)t * S_pad * G;
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
         }
         st_vec<G>(gam_s + (size_t)row * G, out);
       };
-      sell_pass_log<G>(p.view[2], P, Q, warp, lane, epi_gam);
+      sell_pass_log<G, L1C>(p.view[2], P, Q, warp, lane, epi_gam);
       __syncthreads();  // gamma rows complete; everybody done reading P
 
       auto epi_bwd = [&](int row, const float (&o)[G]) {
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
         for (int g = 0; g < G; g++) out[g] = (o[g] > -INFINITY && t < Lg[g]) ? o[g] - sct[g] : -INFINITY;
         st_vec<G>(P + (size_t)row * G, out);
       };
-      sell_pass_log<G>(p.view[1], Q, x_s, warp, lane, epi_bwd);
+      sell_pass_log<G, L1C>(p.view[1], Q, x_s, warp, lane, epi_bwd);
       for (int g = 0; g < G; g++) {  // this frame's gradient rows, coalesced over pdfs
         if (b0 + g >= p.B) break;
         float *gr = p.grad + ((size_t)(b0 + g) * T + t) * D;
@@ -388,17 +388,24 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
   }
 }
 
-int launch_den_shared_log(const BlobHeader &h, const DenParams &p, int G, int grid, size_t smem, cudaStream_t stream) {
+int launch_den_shared_log(const BlobHeader &h, const DenParams &p, int G, bool l1c, int grid, size_t smem,
+                          cudaStream_t stream) {
   cudaError_t e;
-#define LAUNCH_LOG(GG)                                                                                              \
-  do {                                                                                                              \
-    e = cudaFuncSetAttribute(den_shared_log_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    if (e != cudaSuccess) return (int)e;                                                                            \
-    den_shared_log_kernel<GG><<<grid, DEN_NT, smem, stream>>>(p);                                                   \
+#define LAUNCH_LOG(GG, LL)                                                                                              \
+  do {                                                                                                                  \
+    e = cudaFuncSetAttribute(den_shared_log_kernel<GG, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e != cudaSuccess) return (int)e;                                                                                \
+    den_shared_log_kernel<GG, LL><<<grid, DEN_NT, smem, stream>>>(p);                                                   \
   } while (0)
-  if (G == 4) LAUNCH_LOG(4);
-  else if (G == 2) LAUNCH_LOG(2);
-  else LAUNCH_LOG(1);
+  if (l1c) {
+    if (G == 4) LAUNCH_LOG(4, true);
+    else if (G == 2) LAUNCH_LOG(2, true);
+    else LAUNCH_LOG(1, true);
+  } else {
+    if (G == 4) LAUNCH_LOG(4, false);
+    else if (G == 2) LAUNCH_LOG(2, false);
+    else LAUNCH_LOG(1, false);
+  }
 #undef LAUNCH_LOG
   (void)h;
   return (int)cudaGetLastError();

@@ -102,7 +102,18 @@ def _lengths_dev(lengths, device, B):
     return lengths.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
 
 
-def _run_generic(log_domain, graph_tensors, x, lengths, num_states, leaky_coefficient, flags, want_logp=True):
+def _launch_stream(dev, stream):
+    """cudaStream_t to launch on.  With a side `stream`, everything enqueued so far on the current
+    stream (input uploads, the producer of x) is ordered before the launch."""
+    cur = torch.cuda.current_stream(dev)
+    if stream is None or stream == cur:
+        return cur, ctypes.c_void_p(cur.cuda_stream)
+    stream.wait_stream(cur)
+    return stream, ctypes.c_void_p(stream.cuda_stream)
+
+
+def _run_generic(log_domain, graph_tensors, x, lengths, num_states, leaky_coefficient, flags, want_logp=True,
+                 stream=None):
     global _launches
     lib = _cabi.lib()
     what = "nnet_output" if log_domain else "exp_nnet_output"
@@ -124,18 +135,21 @@ def _run_generic(log_domain, graph_tensors, x, lengths, num_states, leaky_coeffi
     diag = torch.empty(2, dtype=torch.float32, device=dev)
     ws_bytes = lib.chain_b200_workspace_bytes(B, T, D, S, K, flags)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    tstream, cstream = _launch_stream(dev, stream)
     if log_domain:
         st = lib.chain_b200_forward_backward_log_domain(
             *[_ptr(t) for t in g], _ptr(x), _ptr(ldev), B, T, D, S, K, flags,
-            _ptr(objf), _ptr(logp), _ptr(grad), _ptr(ok), _ptr(diag), _ptr(ws), ws_bytes, dev.index or 0, stream)
+            _ptr(objf), _ptr(logp), _ptr(grad), _ptr(ok), _ptr(diag), _ptr(ws), ws_bytes, dev.index or 0, cstream)
         _cabi.check(st, "chain_b200_forward_backward_log_domain")
     else:
         st = lib.chain_b200_forward_backward(
             *[_ptr(t) for t in g], _ptr(x), _ptr(ldev), B, T, D, S, K, float(leaky_coefficient), flags,
-            _ptr(objf), _ptr(logp), _ptr(grad), _ptr(ok), _ptr(diag), _ptr(ws), ws_bytes, dev.index or 0, stream)
+            _ptr(objf), _ptr(logp), _ptr(grad), _ptr(ok), _ptr(diag), _ptr(ws), ws_bytes, dev.index or 0, cstream)
         _cabi.check(st, "chain_b200_forward_backward")
     _launches += lib.chain_b200_last_launch_count()
+    if stream is not None:  # buffers of the current stream's pool used by kernels on `stream`
+        for t in (ws, x, ldev):
+            t.record_stream(tstream)
     return Result(objf, logp, grad, ok, diag)
 
 
@@ -188,7 +202,7 @@ def prepare_den_graph(graph_tensors, num_states, D, device, log_domain=False):
     return prep
 
 
-def _run_den_shared(prep, x, lengths, leaky_coefficient, flags):
+def _run_den_shared(prep, x, lengths, leaky_coefficient, flags, stream=None):
     global _launches
     lib = _cabi.lib()
     _require_cuda(x, "exp_nnet_output" if flags & X_IS_EXP else "nnet_output")
@@ -204,12 +218,15 @@ def _run_den_shared(prep, x, lengths, leaky_coefficient, flags):
     diag = torch.empty(2, dtype=torch.float32, device=dev)
     ws_bytes = lib.chain_b200_den_workspace_bytes(_ptr(prep.blob_host), B, T)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    tstream, cstream = _launch_stream(dev, stream)
     st = lib.chain_b200_den_forward_backward(
         _ptr(prep.blob_host), _ptr(prep.blob_dev), prep.copies, _ptr(x), _ptr(ldev), B, T, D, float(leaky_coefficient), flags,
-        _ptr(objf), _ptr(logp), _ptr(grad), _ptr(ok), _ptr(diag), _ptr(ws), ws_bytes, dev.index or 0, stream)
+        _ptr(objf), _ptr(logp), _ptr(grad), _ptr(ok), _ptr(diag), _ptr(ws), ws_bytes, dev.index or 0, cstream)
     _cabi.check(st, "chain_b200_den_forward_backward")
     _launches += lib.chain_b200_last_launch_count()
+    if stream is not None:
+        for t in (ws, x, ldev):
+            t.record_stream(tstream)
     return Result(objf, logp, grad, ok, diag)
 
 
@@ -218,7 +235,7 @@ DEN_PATH = "auto"  # "auto": shared graphs use the packed shared-graph kernels; 
 
 
 def forward_backward_prob(graph_tensors, x, lengths, num_states, leaky_coefficient=1e-5, x_is_exp=True, clamp=False,
-                          path=None):
+                          path=None, stream=None):
     """Probability-domain (denominator) forward-backward.  `graph_tensors` in
     _GRAPH_NAMES_PROB order, reference layout."""
     flags = (X_IS_EXP if x_is_exp else 0) | (CLAMP_X if clamp else 0)
@@ -226,11 +243,11 @@ def forward_backward_prob(graph_tensors, x, lengths, num_states, leaky_coefficie
     B = x.size(0)
     if path != "generic" and _is_shared(graph_tensors, B):
         prep = prepare_den_graph(graph_tensors, num_states, x.size(2), x.device)
-        return _run_den_shared(prep, x, lengths, leaky_coefficient, flags)
-    return _run_generic(False, graph_tensors, x, lengths, num_states, leaky_coefficient, flags)
+        return _run_den_shared(prep, x, lengths, leaky_coefficient, flags, stream=stream)
+    return _run_generic(False, graph_tensors, x, lengths, num_states, leaky_coefficient, flags, stream=stream)
 
 
-def forward_backward_log(graph_tensors, x, lengths, num_states, grad_as_log=True, clamp=False, path=None):
+def forward_backward_log(graph_tensors, x, lengths, num_states, grad_as_log=True, clamp=False, path=None, stream=None):
     """Log-domain (numerator) forward-backward.  `graph_tensors` in _GRAPH_NAMES_LOG order.
     A graph shared by the whole batch (stride-0 views) with >= 256 arcs runs on the packed
     shared-graph kernels, per-utterance graphs on the general kernel."""
@@ -240,5 +257,5 @@ def forward_backward_log(graph_tensors, x, lengths, num_states, grad_as_log=True
     if (path != "generic" and x.size(0) > 1 and _is_shared(graph_tensors, x.size(0)) and K >= 256
             and S <= 32767 and x.size(2) <= 32767):
         prep = prepare_den_graph(graph_tensors, num_states, x.size(2), x.device, log_domain=True)
-        return _run_den_shared(prep, x, lengths, 0.5, flags)
-    return _run_generic(True, graph_tensors, x, lengths, num_states, 0.0, flags)
+        return _run_den_shared(prep, x, lengths, 0.5, flags, stream=stream)
+    return _run_generic(True, graph_tensors, x, lengths, num_states, 0.0, flags, stream=stream)

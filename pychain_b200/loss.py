@@ -59,28 +59,18 @@ class ChainFunction(torch.autograd.Function):
             )
         lengths = _check_lengths(input, input_lengths)
 
-        def run():
-            if not graphs.log_domain:  # usually for the denominator
-                g = tuple(getattr(graphs, n) for n in engine._GRAPH_NAMES_PROB)
-                return engine.forward_backward_prob(g, input, lengths, graphs.num_states, leaky_coefficient,
-                                                    x_is_exp=False, clamp=True)
-            # usually for the numerator
+        # ChainLoss overlaps numerator and denominator: with a side stream set, the kernels are launched
+        # there (outputs and workspace still come from the caller's stream pool; the caller joins the
+        # side stream before using the results), and the autograd node stays on the caller's stream.
+        side = getattr(_tls, "side_stream", None) if input.is_cuda else None
+        if not graphs.log_domain:  # usually for the denominator
+            g = tuple(getattr(graphs, n) for n in engine._GRAPH_NAMES_PROB)
+            r = engine.forward_backward_prob(g, input, lengths, graphs.num_states, leaky_coefficient,
+                                             x_is_exp=False, clamp=True, stream=side)
+        else:  # usually for the numerator
             g = tuple(getattr(graphs, n) for n in engine._GRAPH_NAMES_LOG)
-            return engine.forward_backward_log(g, input, lengths, graphs.num_states, grad_as_log=False, clamp=True)
-
-        side = getattr(_tls, "side_stream", None)
-        if side is not None and input.is_cuda:
-            # launch on the side stream (ChainLoss overlaps numerator and denominator); the autograd
-            # node itself still belongs to the caller's stream, which joins `side` before using the results
-            main = torch.cuda.current_stream(input.device)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                r = run()
-            input.record_stream(side)
-            for t in (r.objf, r.grad, r.ok):
-                t.record_stream(main)
-        else:
-            r = run()
+            r = engine.forward_backward_log(g, input, lengths, graphs.num_states, grad_as_log=False, clamp=True,
+                                            stream=side)
         ctx.save_for_backward(r.grad)
         ctx.mark_non_differentiable(r.ok)
         ChainFunction.last_ok = r.ok  # device int32[1]; not synchronised (the reference ignores `ok`, loss.py:44,62)
