@@ -420,11 +420,12 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         if (lane == 0) red[warp * G + g] = lpart[g];
       }
       // write this frame's gradient rows (coalesced over pdfs) while the other warps finish
-      for (int g = 0; g < G; g++) {
-        if (b0 + g >= p.B) break;
-        float *gr = p.grad + ((size_t)(b0 + g) * T + t) * D;
-        const bool live = t < Lg[g];
-        for (int n = tid; n < D; n += DEN_NT) gr[n] = live ? gam_s[(size_t)n * G + g] : 0.f;
+      for (int n = tid; n < D; n += DEN_NT) {  // one vector read per pdf, G coalesced row writes
+        float v[G];
+        ld_vec<G>(gam_s + (size_t)n * G, v);
+#pragma unroll
+        for (int g = 0; g < G; g++)
+          if (b0 + g < p.B) p.grad[((size_t)(b0 + g) * T + t) * D + n] = (t < Lg[g]) ? v[g] : 0.f;
       }
       __syncthreads();  // beta' rows + partials visible; everybody done reading Q and gam_s
       float cb[G];

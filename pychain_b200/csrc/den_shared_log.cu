@@ -355,12 +355,15 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
         st_vec<G>(P + (size_t)row * G, out);
       };
       sell_pass_log<G, L1C>(p.view[1], Q, x_s, warp, lane, epi_bwd);
-      for (int g = 0; g < G; g++) {  // this frame's gradient rows, coalesced over pdfs
-        if (b0 + g >= p.B) break;
-        float *gr = p.grad + ((size_t)(b0 + g) * T + t) * D;
+      {  // this frame's gradient rows: one vector read per pdf, G coalesced row writes
         const float dead = as_log ? -INFINITY : 0.f;
-        const bool live = t < Lg[g];
-        for (int n = tid; n < D; n += DEN_NT) gr[n] = live ? gam_s[(size_t)n * G + g] : dead;
+        for (int n = tid; n < D; n += DEN_NT) {
+          float v[G];
+          ld_vec<G>(gam_s + (size_t)n * G, v);
+#pragma unroll
+          for (int g = 0; g < G; g++)
+            if (b0 + g < p.B) p.grad[((size_t)(b0 + g) * T + t) * D + n] = (t < Lg[g]) ? v[g] : dead;
+        }
       }
       if (t == 0) {
         float z[G];
