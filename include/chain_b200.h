@@ -41,8 +41,10 @@
  *   x            f32   [B,T,D]   row-major, contiguous
  *   lengths      int64 [B]       valid frames per sequence, 0 <= len <= T
  * with Bg = 1 when CHAIN_B200_GRAPH_SHARED is set (batch stride 0), else Bg = B.
- * Limits: S <= 65535 (the reference's own grid.y limit, chain-computation.cc:126-127),
- * D <= 65535, and 3*S + D floats must fit in 227 KB of shared memory.
+ * Limits: S <= 65535 (the reference's own grid.y limit, chain-computation.cc:126-127) and
+ * D <= 57000.  The general entry points keep their state rows in shared memory when
+ * 3*S + D floats fit in 227 KB and in global memory (slower) otherwise; the packed
+ * shared-graph path needs 2*S + 3*D floats on chip (S up to ~27000 at D = 1000).
  */
 #ifndef CHAIN_B200_H_
 #define CHAIN_B200_H_

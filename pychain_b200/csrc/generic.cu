@@ -39,6 +39,7 @@ struct GenericParams {
   const uint2 *pdf_rec;       // [Bg][K]  {src | dst<<16, weight bits}   arcs sorted by pdf
   const uint2 *bwd_rec;       // [Bg][K]  {src | pdf<<16, weight bits}   backward-CSR order (alpha pass)
   const uint2 *fwd_rec;       // [Bg][K]  {dst | pdf<<16, weight bits}   forward-CSR order (beta pass)
+  float *rows_ws;             // [B][3S+D] state rows + frame in global memory (graphs too large for shared memory)
 };
 
 // ---------------------------------------------------------------- pdf-sorted view
@@ -132,7 +133,10 @@ __device__ __forceinline__ float load_x(const float *__restrict__ p, unsigned fl
 
 // NT threads per CTA: 128 for small per-utterance graphs (numerators; cheap barriers),
 // 1024 for graphs with hundreds of states (one state per thread).
-template <bool LOG, int GEN_NT>
+// GROWS: the three state rows and the frame live in global memory (L2) instead of shared memory --
+// the slow but complete path for graphs whose 3S+D floats exceed 227 KB (up to the 65535-state
+// limit the reference itself has, chain-computation.cc:126-127).
+template <bool LOG, int GEN_NT, bool GROWS = false>
 __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericParams p) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float scratch[64];
@@ -160,7 +164,8 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
   const int L = (int)(Lraw < 0 ? 0 : (Lraw > T ? T : Lraw));
   const float c = p.coeff;
 
-  float *bufA = smem, *bufB = smem + S, *bufC = smem + 2 * S, *x_s = smem + 3 * S;
+  float *rows = GROWS ? p.rows_ws + (size_t)blockIdx.x * ((size_t)3 * S + D) : smem;
+  float *bufA = rows, *bufB = rows + S, *bufC = rows + 2 * S, *x_s = rows + 3 * S;
   double logp = 0.0;  // only thread 0's copy is used
 
   // ------------------------------------------------------------ forward, t = 0
@@ -394,8 +399,10 @@ void launch_finalize(const float *logp, const float *diag, int B, int check_ab, 
 
 // ---------------------------------------------------------------- host side
 struct GenericWs {
-  size_t alpha, tot, pdf_ptr, pdf_rec, bwd_rec, fwd_rec, logp, diag, total;
+  size_t alpha, tot, pdf_ptr, pdf_rec, bwd_rec, fwd_rec, logp, diag, rows, total;
 };
+
+static bool generic_rows_in_global(int S, int D) { return sizeof(float) * ((size_t)3 * S + D) > 227 * 1024 - 1024; }
 
 static GenericWs generic_ws_layout(int B, int T, int D, int S, int K, unsigned flags) {
   GenericWs w;
@@ -409,6 +416,8 @@ static GenericWs generic_ws_layout(int B, int T, int D, int S, int K, unsigned f
   w.fwd_rec = off; off = align_up(off + sizeof(uint2) * Bg * (size_t)(K > 0 ? K : 1));
   w.logp = off; off = align_up(off + sizeof(float) * (size_t)B);
   w.diag = off; off = align_up(off + sizeof(float) * 2 * (size_t)B);
+  w.rows = off;
+  if (generic_rows_in_global(S, D)) off = align_up(off + sizeof(float) * (size_t)B * ((size_t)3 * S + D));
   w.total = off;
   return w;
 }
@@ -428,9 +437,10 @@ static int run_generic(const int32_t *ft, const int32_t *fi, const float *fp, co
   if (S > 65535 || D > 65535) return CHAIN_B200_ERR_UNSUPPORTED;
   const GenericWs w = generic_ws_layout(B, T, D, S, K, flags);
   if (!ws || ws_bytes < w.total) return CHAIN_B200_ERR_WORKSPACE;
-  const size_t smem = sizeof(float) * ((size_t)3 * S + D);
-  if (smem > 227 * 1024 - 1024) return CHAIN_B200_ERR_UNSUPPORTED;
+  const bool grows = generic_rows_in_global(S, D);
+  const size_t smem = grows ? 0 : sizeof(float) * ((size_t)3 * S + D);
   const size_t sort_smem = sizeof(int) * (size_t)(D + 1);
+  if (sort_smem > 227 * 1024 - 1024) return CHAIN_B200_ERR_UNSUPPORTED;
 
   DeviceGuard guard(device);
   if (guard.err != cudaSuccess) return (int)guard.err;
@@ -461,11 +471,13 @@ static int run_generic(const int32_t *ft, const int32_t *fi, const float *fp, co
   p.pdf_rec = (const uint2 *)(base + w.pdf_rec);
   p.bwd_rec = (const uint2 *)(base + w.bwd_rec);
   p.fwd_rec = (const uint2 *)(base + w.fwd_rec);
+  p.rows_ws = (float *)(base + w.rows);
 
-  const int nt = (S <= 160) ? 128 : (S <= 448 ? 256 : 1024);
+  const int nt = grows ? 1024 : ((S <= 160) ? 128 : (S <= 448 ? 256 : 1024));
   void (*kern)(const GenericParams) = chain_generic_kernel<LOG, 256>;
   if (nt == 128) kern = chain_generic_kernel<LOG, 128>;
   if (nt == 1024) kern = chain_generic_kernel<LOG, 1024>;
+  if (grows) kern = chain_generic_kernel<LOG, 1024, true>;
   if (smem > 48 * 1024) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -491,7 +503,7 @@ const char *chain_b200_status_string(int status) {
     case CHAIN_B200_OK: return "ok";
     case CHAIN_B200_ERR_INVALID_ARG: return "invalid argument";
     case CHAIN_B200_ERR_WORKSPACE: return "workspace missing or too small";
-    case CHAIN_B200_ERR_UNSUPPORTED: return "graph too large for the on-chip working set (S,D <= 65535; 3S+D floats <= 226 KB)";
+    case CHAIN_B200_ERR_UNSUPPORTED: return "graph too large (S, D <= 65535; log-domain packed graphs S, D <= 32767; D <= 57000)";
     case CHAIN_B200_ERR_BAD_BLOB: return "not a chain_b200 prepared-graph blob";
     default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown error";
   }

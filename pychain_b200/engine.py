@@ -230,6 +230,13 @@ def _run_den_shared(prep, x, lengths, leaky_coefficient, flags, stream=None):
     return Result(objf, logp, grad, ok, diag)
 
 
+def _shared_fits(S, D):
+    """Working set of the packed shared-graph kernels at G=1 (2 state rows + 3 frame rows, padded
+    to 4) against the 227 KB of shared memory; larger graphs take the general kernel."""
+    pad = lambda n: (n + 3) // 4 * 4  # noqa: E731
+    return 4 * (2 * pad(S) + 3 * pad(D)) + 4096 <= 227 * 1024 and S <= 65535 and D <= 65535
+
+
 # ------------------------------------------------------------------ public helpers
 DEN_PATH = "auto"  # "auto": shared graphs use the packed shared-graph kernels; "generic": always the per-sequence kernel
 
@@ -241,7 +248,7 @@ def forward_backward_prob(graph_tensors, x, lengths, num_states, leaky_coefficie
     flags = (X_IS_EXP if x_is_exp else 0) | (CLAMP_X if clamp else 0)
     path = path or DEN_PATH
     B = x.size(0)
-    if path != "generic" and _is_shared(graph_tensors, B):
+    if path != "generic" and _is_shared(graph_tensors, B) and _shared_fits(int(num_states), int(x.size(2))):
         prep = prepare_den_graph(graph_tensors, num_states, x.size(2), x.device)
         return _run_den_shared(prep, x, lengths, leaky_coefficient, flags, stream=stream)
     return _run_generic(False, graph_tensors, x, lengths, num_states, leaky_coefficient, flags, stream=stream)
@@ -255,7 +262,7 @@ def forward_backward_log(graph_tensors, x, lengths, num_states, grad_as_log=True
     path = path or DEN_PATH
     S, K = int(num_states), int(graph_tensors[0].size(1))
     if (path != "generic" and x.size(0) > 1 and _is_shared(graph_tensors, x.size(0)) and K >= 256
-            and S <= 32767 and x.size(2) <= 32767):
+            and S <= 32767 and x.size(2) <= 32767 and _shared_fits(S, int(x.size(2)))):
         prep = prepare_den_graph(graph_tensors, num_states, x.size(2), x.device, log_domain=True)
         return _run_den_shared(prep, x, lengths, 0.5, flags, stream=stream)
     return _run_generic(True, graph_tensors, x, lengths, num_states, 0.0, flags, stream=stream)

@@ -83,7 +83,31 @@ def test_error_codes_not_crashes(cuda):
     st = lib.chain_b200_forward_backward(*[p(t) for t in dev], p(xd), p(ld), 2, 5, 8, 10, 30, 1e-5, _cabi.GRAPH_SHARED,
                                          p(out), None, p(grad), p(ok), None, None, 0, 0, None)
     assert st == _cabi.ERR_WORKSPACE
-    # a graph whose working set cannot fit on chip -> UNSUPPORTED, not a launch failure
-    assert lib.chain_b200_forward_backward(*[p(t) for t in dev], p(xd), p(ld), 2, 5, 8, 60000, 30, 1e-5, _cabi.GRAPH_SHARED,
+    # more pdfs than the pdf-sort kernel can count on chip -> UNSUPPORTED, not a launch failure
+    assert lib.chain_b200_forward_backward(*[p(t) for t in dev], p(xd), p(ld), 2, 5, 60000, 10, 30, 1e-5, _cabi.GRAPH_SHARED,
                                            p(out), None, p(grad), p(ok), None, p(grad), 1 << 40, 0, None) == _cabi.ERR_UNSUPPORTED
     torch.cuda.synchronize()
+
+
+def test_graph_too_large_for_shared_memory(cuda):
+    """19k states: 3S+D floats exceed 227 KB, so the general kernel keeps its rows in global memory;
+    the packed shared-graph kernels still fit at G=1.  Both must match the oracle."""
+    S, K, D, B, T = 19000, 60000, 40, 2, 5
+    g = ChainGraph(synth.random_den_fst(S, K, D, seed=8))
+    x, lengths = synth.make_inputs(B, T, D, seed=9, variable=True)
+    gb = ChainGraphBatch(g, B)
+    o_c, _, g_c, _, _ = co.den_c(gb, x.clamp(-30, 30).exp(), lengths, 1e-5)
+    gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_PROB)
+    for path in ("generic", "auto"):
+        r = engine.forward_backward_prob(gt, x.to(cuda), lengths, S, 1e-5, x_is_exp=False, clamp=True, path=path)
+        assert rel(r.objf.item(), o_c) < 5e-6
+        assert (r.grad.cpu() - g_c).abs().max().item() < 2e-5
+        assert int(r.ok.item()) == 1
+    # 40k states do not fit the shared-graph kernels at all: the engine falls back by itself
+    S2 = 40000
+    g2 = ChainGraph(synth.random_den_fst(S2, 90000, D, seed=10))
+    gb2 = ChainGraphBatch(g2, B)
+    o2, _, gc2, _, _ = co.den_c(gb2, x.clamp(-30, 30).exp(), lengths, 1e-5)
+    gt2 = tuple(getattr(gb2, n) for n in engine._GRAPH_NAMES_PROB)
+    r = engine.forward_backward_prob(gt2, x.to(cuda), lengths, S2, 1e-5, x_is_exp=False, clamp=True)
+    assert rel(r.objf.item(), o2) < 5e-6 and (r.grad.cpu() - gc2).abs().max().item() < 2e-5
