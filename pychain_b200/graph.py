@@ -227,7 +227,26 @@ class ChainGraph(object):
 
 class ChainGraphBatch(object):
     """A batch of graphs in the reference's padded `[B, ...]` layout
-    (`graph.py:73-194`).  Same constructor, same attributes, same `reorder`."""
+    (`graph.py:73-194`).  Same constructor arguments, attributes and `reorder`.
+
+    The per-graph tensors are described once, in `_FIELDS`: (name, trailing shape in terms of
+    K = transitions / S = states, pad value in the probability domain, pad value in the log
+    domain); both constructors and `reorder` / `to` / `materialize` are driven by that table.
+    """
+
+    #        name                            shape        pad(prob)  pad(log)
+    _FIELDS = (
+        ("forward_transitions",            ("K", 3),     0,         0),
+        ("forward_transition_indices",     ("S", 2),     0,         0),
+        ("forward_transition_probs",       ("K",),       0.0,       0.0),
+        ("backward_transitions",           ("K", 3),     0,         0),
+        ("backward_transition_indices",    ("S", 2),     0,         0),
+        ("backward_transition_probs",      ("K",),       0.0,       0.0),
+        ("leaky_probs",                    ("S",),       0.0,       None),       # absent in the log domain
+        ("initial_probs",                  ("S",),       0.0,       float("-inf")),
+        ("final_probs",                    ("S",),       0.0,       float("-inf")),
+    )
+    _BATCH_FIELDS = tuple(f[0] for f in _FIELDS) + ("start_state",)
 
     def __init__(self, graphs, batch_size=None, max_num_transitions=None, max_num_states=None):
         self.shared_graph = None  # the single ChainGraph when all B rows are the same graph
@@ -237,97 +256,59 @@ class ChainGraphBatch(object):
             self.batch_size = batch_size
             self.initialized_by_one(graphs)
         elif isinstance(graphs, (list, ChainGraph)):
-            if not max_num_transitions:
-                raise ValueError(
-                    "max_num_transitions should be specified if given a "
-                    "a list of ChainGraph objects to initialize from"
-                )
-            if not max_num_states:
-                raise ValueError(
-                    "max_num_states should be specified if given a "
-                    "a list of ChainGraph objects to initialize from"
-                )
+            for value, name in ((max_num_transitions, "max_num_transitions"), (max_num_states, "max_num_states")):
+                if not value:
+                    raise ValueError(
+                        "{} should be specified if given a a list of ChainGraph objects to initialize from".format(name))
             self.batch_size = len(graphs)
             self.initialized_by_list(graphs, max_num_transitions, max_num_states)
         else:
             raise ValueError(
-                "ChainGraphBatch should be either initialized by a "
-                "single ChainGraph object or a list of ChainGraph objects "
-                "but given {}".format(type(graphs))
-            )
+                "ChainGraphBatch should be either initialized by a single ChainGraph object or a list of "
+                "ChainGraph objects but given {}".format(type(graphs)))
 
     def initialized_by_one(self, graph):
-        """Reference `graph.py:101-120` repeats the graph B times; here every
-        batch tensor is a stride-0 view of the one graph (same shapes)."""
-        self.log_domain = graph.log_domain
-        self.shared_graph = graph
+        """One graph for the whole batch.  The reference repeats it B times
+        (`graph.py:101-120`); here every batch tensor is a stride-0 view of the one graph
+        (same shapes, O(1) memory), which is also how the engine recognises a shared graph."""
         B = self.batch_size
-
-        def ex(t):
-            return t.unsqueeze(0).expand(B, *t.shape)
-
-        self.forward_transitions = ex(graph.forward_transitions)
-        self.forward_transition_indices = ex(graph.forward_transition_indices)
-        self.forward_transition_probs = ex(graph.forward_transition_probs)
-        self.backward_transitions = ex(graph.backward_transitions)
-        self.backward_transition_indices = ex(graph.backward_transition_indices)
-        self.backward_transition_probs = ex(graph.backward_transition_probs)
-        self.num_states = graph.num_states
-        self.num_transitions = graph.num_transitions
-        self.final_probs = ex(graph.final_probs)
-        self.leaky_probs = ex(graph.leaky_probs) if not self.log_domain else None
-        self.initial_probs = ex(graph.initial_probs)
-        self.start_state = graph.start_state * torch.ones(B, dtype=torch.long)
+        self.shared_graph = graph
+        self.log_domain = graph.log_domain
+        self.num_states, self.num_transitions = graph.num_states, graph.num_transitions
+        for name, _, _, pad_log in self._FIELDS:
+            t = getattr(graph, name)
+            setattr(self, name, None if t is None else t.unsqueeze(0).expand(B, *t.shape))
+        self.start_state = torch.full((B,), int(graph.start_state), dtype=torch.long)
 
     def initialized_by_list(self, graphs, max_num_transitions, max_num_states):
-        """Zero / -inf padded stack, as reference `graph.py:122-175`."""
-        transition_type = graphs[0].forward_transitions.dtype
-        probs_type = graphs[0].forward_transition_probs.dtype
-        self.log_domain = graphs[0].log_domain
-        self.num_states = max_num_states
-        self.num_transitions = max_num_transitions
+        """Per-utterance graphs stacked with zero / -inf padding (`graph.py:122-175`): padded
+        states have empty (0,0) arc ranges and no initial / final mass."""
         B = self.batch_size
-        self.forward_transitions = torch.zeros([B, max_num_transitions, 3], dtype=transition_type)
-        self.forward_transition_indices = torch.zeros([B, max_num_states, 2], dtype=transition_type)
-        self.forward_transition_probs = torch.zeros([B, max_num_transitions], dtype=probs_type)
-        self.backward_transitions = torch.zeros([B, max_num_transitions, 3], dtype=transition_type)
-        self.backward_transition_indices = torch.zeros([B, max_num_states, 2], dtype=transition_type)
-        self.backward_transition_probs = torch.zeros([B, max_num_transitions], dtype=probs_type)
-        if self.log_domain:
-            self.leaky_probs = None  # no leaky hmm if in log domain
-            self.initial_probs = torch.full([B, max_num_states], float("-inf"), dtype=probs_type)
-            self.final_probs = torch.full([B, max_num_states], float("-inf"), dtype=probs_type)
-        else:
-            self.leaky_probs = torch.zeros([B, max_num_states], dtype=probs_type)
-            self.initial_probs = torch.zeros([B, max_num_states], dtype=probs_type)
-            self.final_probs = torch.zeros([B, max_num_states], dtype=probs_type)
+        self.log_domain = graphs[0].log_domain
+        self.num_states, self.num_transitions = max_num_states, max_num_transitions
+        dims = {"K": max_num_transitions, "S": max_num_states}
+        for name, shape, pad_prob, pad_log in self._FIELDS:
+            pad = pad_log if self.log_domain else pad_prob
+            if pad is None:
+                setattr(self, name, None)
+                continue
+            like = getattr(graphs[0], name)
+            full = [B] + [dims.get(d, d) for d in shape]
+            setattr(self, name, torch.full(full, pad, dtype=like.dtype))
         self.start_state = torch.zeros([B], dtype=torch.long)
-
         for i, graph in enumerate(graphs):
             nt, ns = graph.num_transitions, graph.num_states
             if nt > max_num_transitions or ns > max_num_states:
                 raise ValueError("graph {} ({} states, {} transitions) exceeds the batch maxima".format(i, ns, nt))
-            self.forward_transitions[i, :nt, :].copy_(graph.forward_transitions)
-            self.forward_transition_indices[i, :ns, :].copy_(graph.forward_transition_indices)
-            self.forward_transition_probs[i, :nt].copy_(graph.forward_transition_probs)
-            self.backward_transitions[i, :nt, :].copy_(graph.backward_transitions)
-            self.backward_transition_indices[i, :ns, :].copy_(graph.backward_transition_indices)
-            self.backward_transition_probs[i, :nt].copy_(graph.backward_transition_probs)
-            if self.leaky_probs is not None:
-                self.leaky_probs[i, :ns].copy_(graph.leaky_probs)
-            self.initial_probs[i, :ns].copy_(graph.initial_probs)
-            self.final_probs[i, :ns].copy_(graph.final_probs)
+            for name, shape, _, _ in self._FIELDS:
+                dst = getattr(self, name)
+                if dst is not None:
+                    dst[i, :(nt if shape[0] == "K" else ns)].copy_(getattr(graph, name))
             self.start_state[i] = graph.start_state
 
-    _BATCH_FIELDS = (
-        "forward_transitions", "forward_transition_indices", "forward_transition_probs",
-        "backward_transitions", "backward_transition_indices", "backward_transition_probs",
-        "leaky_probs", "initial_probs", "final_probs", "start_state",
-    )
-
     def reorder(self, new_order):
-        """Reference `graph.py:177-194`.  For a shared graph every row is the
-        same graph, so the (stride-0) graph tensors are left untouched."""
+        """Select / permute utterances (`graph.py:177-194`).  For a shared graph every row is
+        the same graph, so the (stride-0) graph tensors only change their batch size."""
         if self.shared_graph is not None:
             if new_order.numel() != self.batch_size:
                 self.batch_size = int(new_order.numel())
@@ -340,8 +321,8 @@ class ChainGraphBatch(object):
 
     # -- conveniences that the reference does not have ---------------------------
     def to(self, device):
-        """Move the batch tensors to `device` once, instead of the reference's
-        per-call `.cuda()` inside the extension (`chain-computation.cc:77-89`)."""
+        """Move the batch tensors to `device` once, instead of the reference's per-call
+        `.cuda()` inside the extension (`chain-computation.cc:77-89`)."""
         for name in self._BATCH_FIELDS:
             t = getattr(self, name)
             if t is not None:
@@ -349,9 +330,9 @@ class ChainGraphBatch(object):
         return self
 
     def materialize(self):
-        """Contiguous `[B, ...]` copies (what the reference's `.repeat` makes);
-        needed only to hand a shared-graph batch to the *reference* extension,
-        whose CHECK_CONTIGUOUS (`pychain.cc:42-54`) rejects stride-0 views."""
+        """Contiguous `[B, ...]` copies (what the reference's `.repeat` makes); needed only to
+        hand a shared-graph batch to the *reference* extension, whose CHECK_CONTIGUOUS
+        (`pychain.cc:42-54`) rejects stride-0 views."""
         for name in self._BATCH_FIELDS:
             t = getattr(self, name)
             if t is not None:
