@@ -270,6 +270,7 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
   v.n_slices = n_slices;
   v.rows.assign((size_t)n_slices * 32, -1);
   v.width.assign(n_slices, 0);
+  std::vector<long> slice_cost(n_slices, 0);  // modelled shared-memory wavefronts of each slice
   std::vector<std::vector<uint32_t>> s_ab(n_slices);
   std::vector<std::vector<float>> s_w(n_slices);
   const uint32_t na = (uint32_t)n_a, nb = (uint32_t)n_b;
@@ -324,21 +325,29 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
           s_ab[s][pos] = ga | (gb << 16);
           ia[q * 8 + i] = ga; ib[q * 8 + i] = gb;
         }
-        v.predicted += quarter_wavefronts(ia + 8 * q, 8) + quarter_wavefronts(ib + 8 * q, 8);
+        const int wf = quarter_wavefronts(ia + 8 * q, 8) + quarter_wavefronts(ib + 8 * q, 8);
+        v.predicted += wf;
+        slice_cost[s] += wf;
         v.ideal += 2;
       }
     }
   }
 
-  // slices -> warps: longest-processing-time first (slices are sorted by width already)
+  // slices -> warps: longest-processing-time first on the modelled cost of each slice (its
+  // shared-memory wavefronts + a per-slice epilogue constant), so the warps of a CTA reach the
+  // barrier that ends a pass together
+  std::vector<int> by_cost(n_slices);
+  std::iota(by_cost.begin(), by_cost.end(), 0);
+  auto cost_of = [&](int s) { return structure_only ? (long)v.width[s] * 10 + 12 : slice_cost[s] + 12; };
+  std::stable_sort(by_cost.begin(), by_cost.end(), [&](int x, int y) { return cost_of(x) > cost_of(y); });
   std::vector<long> load(DEN_NW, 0);
   std::vector<std::vector<int32_t>> per(DEN_NW);
-  for (int s = 0; s < n_slices; s++) {
+  for (int s : by_cost) {
     int best = 0;
     for (int wv = 1; wv < DEN_NW; wv++)
       if (load[wv] < load[best]) best = wv;
     per[best].push_back(s);
-    load[best] += v.width[s] + 4;
+    load[best] += cost_of(s);
   }
   v.warp_info.assign((size_t)DEN_NW * 3, 0);
   v.rec_ab.clear();
