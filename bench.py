@@ -396,6 +396,16 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "note": "algorithmic bytes = F*(12D+8S) (x2 for the full loss: numerator + denominator); the kernels are shared-memory-gather / latency bound, see DESIGN.md"}
 
+    # secondary ceiling: the kernels gather 6 fp32 operands per arc and valid frame from
+    # shared memory (alpha/x, beta/x, alpha/beta); peak = SMs x 128 B/clk x SM clock
+    sm_clock = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+    smem_peak = torch.cuda.get_device_properties(dev).multi_processor_count * 128.0 * sm_clock / 1e9
+    gather_bytes = 24.0 * K * frames
+    roofline["secondary"] = {"bound": "shared-memory gathers", "achieved": gather_bytes / (kern_ms * 1e-3) / 1e9,
+                             "peak": smem_peak, "unit": "GB/s",
+                             "frac": gather_bytes / (kern_ms * 1e-3) / 1e9 / smem_peak,
+                             "bytes_per_launch": gather_bytes}
+
     cpu_baseline = None
     if not a.no_cpu_baseline and world == 1:
         try:

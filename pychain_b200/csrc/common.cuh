@@ -95,6 +95,7 @@ __device__ __forceinline__ float block_lse(float m, float s, float *scratch /* >
   return (M == -INFINITY) ? -INFINITY : M + logf(Sx);
 }
 
-__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+// torch.clamp semantics (loss.py:30): NaN propagates (fminf/fmaxf would silently turn it into a bound)
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 }  // namespace chainb200

@@ -28,6 +28,26 @@ import torch
 from . import _cabi, engine
 
 
+def _report(r, batch, log_domain):
+    """What the reference's self-check prints to stderr (chain-computation.cc:363-390,
+    chain-log-domain-computation.cc:289-303), from the device-side diagnostics: on failure, and
+    always at verbose level >= 1 (the reference re-checks every frame then; here frame 0 is the
+    one that accumulates the whole backward recursion)."""
+    import sys
+    ok = bool(r.ok.item())
+    verbose = _cabi.lib().chain_b200_get_verbose_level() >= 1
+    if ok and not verbose:
+        return ok
+    ab, gs = (float(v) for v in r.diag.tolist())
+    if not log_domain and (verbose or abs(ab - batch) >= ab * 0.01):
+        print("On time 0, alpha-beta product {} != {}".format(ab, batch), file=sys.stderr)
+    if verbose or abs(gs - batch) >= gs * 0.01:
+        print("On time 0, log-prob-deriv sum {} != {}".format(gs, batch), file=sys.stderr)
+    if not ok:
+        print("Excessive error detected, will abandon this minibatch", file=sys.stderr)
+    return ok
+
+
 def _check_contiguous(t, name):
     if t is not None and not (t.is_contiguous() or t.stride(0) == 0):
         raise RuntimeError("{} must be contiguous".format(name))
@@ -45,7 +65,8 @@ def forward_backward(forward_transitions, forward_transition_indices, forward_tr
         _check_contiguous(t, n)
     r = engine.forward_backward_prob(g, exp_nnet_output, sequence_lengths, num_states, leaky_hmm_coefficient,
                                      x_is_exp=True, clamp=False)
-    return [r.objf, r.grad, r.ok.bool().cpu()]
+    ok = _report(r, exp_nnet_output.size(0), False)
+    return [r.objf, r.grad, torch.full((1,), ok, dtype=torch.bool)]
 
 
 def forward_backward_log_domain(forward_transitions, forward_transition_indices, forward_transition_probs,
@@ -58,7 +79,8 @@ def forward_backward_log_domain(forward_transitions, forward_transition_indices,
     for t, n in zip(g, engine._GRAPH_NAMES_LOG):
         _check_contiguous(t, n)
     r = engine.forward_backward_log(g, nnet_output, sequence_lengths, num_states, grad_as_log=True, clamp=False)
-    return [r.objf, r.grad, r.ok.bool().cpu()]
+    ok = _report(r, nnet_output.size(0), True)
+    return [r.objf, r.grad, torch.full((1,), ok, dtype=torch.bool)]
 
 
 def set_verbose_level(level):

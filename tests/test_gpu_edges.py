@@ -111,3 +111,35 @@ def test_graph_too_large_for_shared_memory(cuda):
     gt2 = tuple(getattr(gb2, n) for n in engine._GRAPH_NAMES_PROB)
     r = engine.forward_backward_prob(gt2, x.to(cuda), lengths, S2, 1e-5, x_is_exp=False, clamp=True)
     assert rel(r.objf.item(), o2) < 5e-6 and (r.grad.cpu() - gc2).abs().max().item() < 2e-5
+
+
+def test_ok_flag_and_verbose_report(cuda, capfd):
+    """Numerical trouble clears `ok` and is reported on stderr like the reference's self-check
+    (chain-computation.cc:363-390); set_verbose_level(1) reports the frame-0 check even when it passes."""
+    g = ChainGraph(synth.random_den_fst(12, 40, 8, seed=2))
+    B, T, D = 3, 7, 8
+    gb = ChainGraphBatch(g, B).materialize()
+    x, lengths = synth.make_inputs(B, T, D, seed=3)
+    args = lambda xx: (gb.forward_transitions, gb.forward_transition_indices, gb.forward_transition_probs,  # noqa: E731
+                       gb.backward_transitions, gb.backward_transition_indices, gb.backward_transition_probs,
+                       gb.leaky_probs, gb.initial_probs, gb.final_probs, gb.start_state,
+                       xx.exp().to(cuda), None, lengths, gb.num_states, 1e-5)
+    objf, grad, ok = new_C.forward_backward(*args(x))
+    assert bool(ok.item()) and capfd.readouterr().err == ""
+    new_C.set_verbose_level(1)
+    try:
+        objf, grad, ok = new_C.forward_backward(*args(x))
+        err = capfd.readouterr().err
+        assert bool(ok.item()) and "alpha-beta product" in err and "log-prob-deriv sum" in err
+    finally:
+        new_C.set_verbose_level(0)
+    bad = x.clone()
+    bad[1, 2, :] = float("nan")
+    objf, grad, ok = new_C.forward_backward(*args(bad))
+    err = capfd.readouterr().err
+    assert not bool(ok.item()) and "Excessive error detected" in err
+    for path in ("generic", "auto"):  # both kernels flag it on the device
+        gs = ChainGraphBatch(g, B)
+        gt = tuple(getattr(gs, n) for n in engine._GRAPH_NAMES_PROB)
+        r = engine.forward_backward_prob(gt, bad.to(cuda), lengths, gs.num_states, 1e-5, x_is_exp=False, clamp=True, path=path)
+        assert int(r.ok.item()) == 0
