@@ -131,3 +131,39 @@ def test_chain_loss_end_to_end(cuda):
     obj = ChainFunction.apply(xd2, lengths, nb)
     (obj * 0.5).backward()
     assert (xd2.grad.cpu() - 0.5 * lg_num.exp()).abs().max().item() < GRAD_ATOL
+
+
+def test_cfg4_full_size_properties(cuda):
+    """BASELINE cfg4 at full size (S=5000, K=40000, B=512, T=200, D=1000): the oracle would need
+    minutes, so check what does not depend on size -- posteriors of every valid frame sum to one,
+    alpha'.beta' = 1 at frame 0, padded frames are exactly zero, group widths agree, and a slice of the
+    batch equals the same utterances run alone."""
+    c = synth.CONFIGS["cfg4"]
+    B, T, D, S = c["B"], c["T"], c["D"], c["S"]
+    g = synth.den_graph_for("cfg4")
+    gb = ChainGraphBatch(g, B)
+    x, lengths = synth.make_inputs(B, T, D, seed=2004, variable=True)
+    xd = x.to(cuda)
+    gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_PROB)
+    r4 = engine.forward_backward_prob(gt, xd, lengths, S, 1e-5, x_is_exp=False, clamp=True)
+    assert int(r4.ok.item()) == 1 and torch.isfinite(r4.objf).item()
+    rows = r4.grad.sum(-1)                                   # [B,T]
+    mask = torch.arange(T, device=cuda)[None, :] < lengths.to(cuda)[:, None]
+    assert (rows[mask] - 1).abs().max().item() < 5e-4
+    assert r4.grad[~mask].abs().max().item() == 0.0
+    assert abs(r4.diag[0].item() - B) < 1e-3 * B and abs(r4.diag[1].item() - B) < 1e-3 * B
+    assert abs(r4.logp.sum().item() - r4.objf.item()) < 1e-3 * abs(r4.objf.item())
+    os.environ["CHAIN_B200_G"] = "2"
+    try:
+        r2 = engine.forward_backward_prob(gt, xd, lengths, S, 1e-5, x_is_exp=False, clamp=True)
+    finally:
+        os.environ.pop("CHAIN_B200_G", None)
+    assert rel(r2.objf.item(), r4.objf.item()) < 2e-6
+    assert (r2.grad - r4.grad).abs().max().item() < GRAD_ATOL
+    # utterances 100..107 alone (another grouping, another position in the batch): same numbers
+    sub = slice(100, 108)
+    gb8 = ChainGraphBatch(g, 8)
+    gt8 = tuple(getattr(gb8, n) for n in engine._GRAPH_NAMES_PROB)
+    r8 = engine.forward_backward_prob(gt8, xd[sub].contiguous(), lengths[sub], S, 1e-5, x_is_exp=False, clamp=True)
+    assert (r8.logp - r4.logp[sub]).abs().max().item() < 2e-3
+    assert (r8.grad - r4.grad[sub]).abs().max().item() < GRAD_ATOL
