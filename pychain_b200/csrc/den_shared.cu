@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
           if (f < Lg[g]) {
             t = p.use_tma_x ? xraw[(size_t)g * D_pad + n] : __ldg(xg[g] + (size_t)f * D + n);
             if (clamp_x) t = clampf(t, kClampLo, kClampHi);
-            if (exp_x) t = __expf(t);
+            if (exp_x) t = expf(t);
           }
           v[g] = t;
         }
