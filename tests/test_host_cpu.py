@@ -238,3 +238,19 @@ def test_den_packer_rejects_bad_graphs():
     assert lib.chain_b200_den_prepare_bytes(p(ft), p(fi), p(bt), p(bi), 70000, 30, 8, 0) == _cabi.ERR_UNSUPPORTED
     assert lib.chain_b200_den_prepare_bytes(p(ft), p(fi), p(bt), p(bi), 40000, 30, 8, _cabi.LOG_DOMAIN) == _cabi.ERR_UNSUPPORTED
     assert lib.chain_b200_den_workspace_bytes(p(torch.zeros(512, dtype=torch.uint8)), 4, 10) == 0  # not a blob
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing in the shipped package may import, load or call it."""
+    pkg = os.path.join(ROOT, "pychain_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            text = open(os.path.join(dirpath, f)).read()
+            for line in text.splitlines():
+                code = line.split("#")[0].split("//")[0]
+                assert not re.search(r"\b(import|from)\s+oracle\b", code), (f, line)
+                assert "chain_oracle" not in code and "oracle/_ref" not in code, (f, line)
+    hdr = open(os.path.join(ROOT, "include", "chain_b200.h")).read()
+    assert "NO CPU implementation" in hdr
