@@ -167,3 +167,21 @@ def test_cfg4_full_size_properties(cuda):
     r8 = engine.forward_backward_prob(gt8, xd[sub].contiguous(), lengths[sub], S, 1e-5, x_is_exp=False, clamp=True)
     assert (r8.logp - r4.logp[sub]).abs().max().item() < 2e-3
     assert (r8.grad - r4.grad[sub]).abs().max().item() < GRAD_ATOL
+
+
+def test_bitwise_reproducible(cuda):
+    """No atomics, fixed reduction orders: two runs give bit-identical objf and gradient
+    (the reference's CUDA denominator gradient is stochastic, chain-kernels.cu:53-87)."""
+    g = ChainGraph(synth.random_den_fst(200, 1600, 40, seed=61, variant="skew"))
+    B, T, D = 13, 30, 40
+    x, lengths = synth.make_inputs(B, T, D, seed=62, variable=True)
+    gb = ChainGraphBatch(g, B)
+    gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_PROB)
+    nb = synth.make_num_batch(B, T, D, seed=63, min_phones=3, max_phones=8)
+    gn = tuple(getattr(nb, n) for n in engine._GRAPH_NAMES_LOG)
+    xd = x.to(cuda)
+    for fn in (lambda: engine.forward_backward_prob(gt, xd, lengths, gb.num_states, 1e-5, x_is_exp=False, clamp=True),
+               lambda: engine.forward_backward_prob(gt, xd, lengths, gb.num_states, 1e-5, x_is_exp=False, clamp=True, path="generic"),
+               lambda: engine.forward_backward_log(gn, xd, lengths, nb.num_states, grad_as_log=False, clamp=True)):
+        a, b = fn(), fn()
+        assert torch.equal(a.objf, b.objf) and torch.equal(a.grad, b.grad) and torch.equal(a.logp, b.logp)
