@@ -68,6 +68,8 @@ extern "C" {
 #define CHAIN_B200_CLAMP_X        4u  /* apply clamp(x,-30,30) (loss.py:30) inside the kernel (x is raw nnet output) */
 #define CHAIN_B200_GRAD_AS_LOG    8u  /* log domain: write log-posteriors (-inf where empty) like the reference;
                                          otherwise write posteriors, i.e. the caller's `.exp()` (loss.py:77) is fused */
+#define CHAIN_B200_PACK_G(g)     ((unsigned)(g) << 8) /* chain_b200_den_prepare*: optimise the record order for groups of
+                                         g = 1, 2 or 4 utterances (default 4); see chain_b200_den_group_width */
 #define CHAIN_B200_LOG_DOMAIN    16u  /* chain_b200_den_prepare*: the graph is a log-domain graph (weights, init, final
                                          are log-probabilities, no leaky HMM; S, D <= 32767) */
 
@@ -136,6 +138,11 @@ int chain_b200_den_prepare(
     int S, int K, int D, unsigned flags, void *blob_host, int64_t blob_bytes);
 
 size_t chain_b200_den_workspace_bytes(const void *blob_host, int B, int T);
+
+/* Utterances per CTA (1, 2 or 4) the shared-graph kernels will use for a batch of B on `device`
+ * (0 if the graph does not fit on chip).  Packing the blob with CHAIN_B200_PACK_G(that value) gives the
+ * record order whose shared-memory bank conflicts are minimised for that group width. */
+int chain_b200_den_group_width(int S, int D, int B, int device);
 
 int chain_b200_den_forward_backward(
     const void *blob_host, const void *blob_dev, int blob_copies,

@@ -27,7 +27,7 @@
 namespace chainb200 {
 
 constexpr uint32_t kBlobMagic = 0x42324348u;  // "HC2B"
-constexpr uint32_t kBlobVersion = 7;
+constexpr uint32_t kBlobVersion = 8;
 #ifndef CHAIN_B200_NW
 #define CHAIN_B200_NW 16
 #endif
@@ -51,6 +51,7 @@ struct BlobView {
 struct BlobHeader {
   uint32_t magic, version;
   int32_t S, K, D, nwarps, S_pad, D_pad, max_sub, log_domain;
+  int32_t opt_G, reserved[3];  // group width whose bank geometry the column order was optimised for
   BlobView view[3];
   int64_t off_leaky, off_init, off_final;
   int64_t total_bytes;

@@ -36,21 +36,26 @@ struct ViewBuild {
   double predicted = 0, ideal = 0;
 };
 
-// Shared-memory wavefronts of one vector gather by a quarter-warp (8 lanes, 16-byte
-// elements => 8 bank groups): the largest number of DISTINCT elements that fall into
-// the same bank group (equal addresses are a broadcast).
-static int quarter_wavefronts(const uint32_t *idx, int n) {
+// Bank geometry of the gathers for a group width G: a vector load of G floats per lane is served in
+// phases of P = 32/G lanes (G=4: quarter-warps of 8 lanes and 16-byte elements, G=2: half-warps of 16
+// lanes and 8-byte elements, G=1: the whole warp and 4-byte elements), and within a phase element e
+// lives in bank group e mod P.  Wavefronts of one phase = the largest number of DISTINCT elements
+// that fall into the same bank group (equal addresses are a broadcast).
+static int phase_wavefronts(const uint32_t *idx, int n, int P) {
   int worst = 1;
-  for (int s = 0; s < 8; s++) {
-    uint32_t seen[8];
-    int ns = 0;
-    for (int i = 0; i < n; i++) {
-      if ((idx[i] & 7u) != (uint32_t)s) continue;
+  const uint32_t mask = (uint32_t)P - 1u;
+  for (int i = 0; i < n; i++) {
+    int cnt = 1;
+    bool first = true;
+    for (int j = 0; j < n; j++) {
+      if (j == i || (idx[j] & mask) != (idx[i] & mask)) continue;
+      if (idx[j] == idx[i]) { if (j < i) first = false; continue; }   // broadcast partner
+      // count distinct elements only once: skip j if an equal element appears earlier
       bool dup = false;
-      for (int j = 0; j < ns; j++) dup |= (seen[j] == idx[i]);
-      if (!dup) seen[ns++] = idx[i];
+      for (int l = 0; l < j; l++) dup |= (idx[l] == idx[j]);
+      if (!dup) cnt++;
     }
-    worst = std::max(worst, ns);
+    if (first) worst = std::max(worst, cnt);
   }
   return worst;
 }
@@ -76,15 +81,17 @@ static int pack_effort(int K) {
   return K <= 120000 ? 4 : (K <= 400000 ? 2 : 1);
 }
 
-// A. Regroup the (length-sorted) units so that every run of 8 consecutive units -- the rows a
-// quarter-warp processes side by side -- has flat histograms of bank groups (index mod 8) for
-// both gathered operands.  Flat histograms are what makes a conflict-free column order exist.
-static void balance_quarters(const std::vector<Unit> &units, std::vector<int> &order) {
+// A. Regroup the (length-sorted) units so that every run of P consecutive units -- the rows one
+// phase of a vector load processes side by side -- has flat histograms of bank groups (index mod P)
+// for both gathered operands and distinct bank groups for its output rows.  Flat histograms are what
+// makes a conflict-free column order exist.
+static void balance_groups(const std::vector<Unit> &units, std::vector<int> &order, int P) {
   const int n = (int)order.size();
-  std::vector<std::array<uint16_t, 16>> hist(units.size());
+  const uint32_t mask = (uint32_t)P - 1u;
+  std::vector<std::array<uint16_t, 64>> hist(units.size());
   for (size_t u = 0; u < units.size(); u++) {
     hist[u].fill(0);
-    for (const Arc &a : units[u].arcs) { hist[u][a.ab & 7u]++; hist[u][8 + ((a.ab >> 16) & 7u)]++; }
+    for (const Arc &a : units[u].arcs) { hist[u][a.ab & mask]++; hist[u][32 + ((a.ab >> 16) & mask)]++; }
   }
   std::vector<int> out;
   out.reserve(n);
@@ -96,13 +103,13 @@ static void balance_quarters(const std::vector<Unit> &units, std::vector<int> &o
     const int first = order[head];
     used[head] = 1;
     out.push_back(first);
-    long sum[16];
-    for (int c = 0; c < 16; c++) sum[c] = hist[first][c];
+    long sum[64];
+    for (int c = 0; c < 64; c++) sum[c] = hist[first][c];
     const size_t len0 = units[first].arcs.size();
-    // bank groups already taken by the output rows of this quarter (the epilogue stores out[row][g])
-    auto out_group = [&](int u) { const int c = units[u].row_code; return (c >= 0 ? c : -2 - c) & 7; };  // row or partial slot
+    // bank groups already taken by the output rows of this group (the epilogue stores out[row][g])
+    auto out_group = [&](int u) { const int c = units[u].row_code; return (uint32_t)(c >= 0 ? c : -2 - c) & mask; };
     unsigned out_used = 1u << out_group(first);
-    for (int pick = 1; pick < 8 && (int)out.size() < n; pick++) {
+    for (int pick = 1; pick < P && (int)out.size() < n; pick++) {
       int best = -1;
       long best_cost = 0;
       int seen = 0;
@@ -113,7 +120,7 @@ static void balance_quarters(const std::vector<Unit> &units, std::vector<int> &o
         if (units[u].arcs.size() + 1 < len0 && seen >= 8) break;
         seen++;
         long cost = 0;
-        for (int c = 0; c < 16; c++) { const long t = sum[c] + hist[u][c]; cost += t * t; }
+        for (int c = 0; c < 64; c++) { const long t = sum[c] + hist[u][c]; cost += t * t; }
         cost = cost * 4 + (long)(len0 - units[u].arcs.size()) * 64;
         if ((out_used >> out_group(u)) & 1u) cost += 24;
         if (best < 0 || cost < best_cost) { best = j; best_cost = cost; }
@@ -122,34 +129,35 @@ static void balance_quarters(const std::vector<Unit> &units, std::vector<int> &o
       used[best] = 1;
       out.push_back(order[best]);
       out_used |= 1u << out_group(order[best]);
-      for (int c = 0; c < 16; c++) sum[c] += hist[order[best]][c];
+      for (int c = 0; c < 64; c++) sum[c] += hist[order[best]][c];
     }
   }
   order.swap(out);
 }
 
-// B. Column order inside one quarter (8 lanes x W columns): simulated annealing over swaps of
+// B. Column order inside one phase group (P lanes x W columns): simulated annealing over swaps of
 // two entries of one lane, minimising the modelled wavefronts sum_k (max multiplicity of the
 // a-bank-groups + max multiplicity of the b-bank-groups), ties broken towards flat counts.
-static void anneal_quarter(const Unit *const *lanes, int W, int *arr /* [8][W] arc index or -1 */, Rng &rng,
-                           int effort) {
-  std::vector<uint8_t> c1((size_t)W * 8, 0), c2((size_t)W * 8, 0);
+static void anneal_group(const Unit *const *lanes, int P, int W, int *arr /* [P][W] arc index or -1 */, Rng &rng,
+                         int effort) {
+  const uint32_t mask = (uint32_t)P - 1u;
+  std::vector<uint8_t> c1((size_t)W * P, 0), c2((size_t)W * P, 0);
   auto col_of = [&](int i, int k, int &x, int &y) {
     const int j = arr[i * W + k];
     if (j < 0) { x = y = -1; return; }
     const uint32_t ab = lanes[i]->arcs[j].ab;
-    x = ab & 7u; y = (ab >> 16) & 7u;
+    x = ab & mask; y = (ab >> 16) & mask;
   };
-  for (int i = 0; i < 8; i++)
+  for (int i = 0; i < P; i++)
     for (int k = 0; k < W; k++) {
       int x, y;
       col_of(i, k, x, y);
-      if (x >= 0) { c1[k * 8 + x]++; c2[k * 8 + y]++; }
+      if (x >= 0) { c1[k * P + x]++; c2[k * P + y]++; }
     }
   auto col_cost = [&](int k) {
     int m1 = 0, m2 = 0, sq = 0;
-    for (int c = 0; c < 8; c++) {
-      const int u = c1[k * 8 + c], v = c2[k * 8 + c];
+    for (int c = 0; c < P; c++) {
+      const int u = c1[k * P + c], v = c2[k * P + c];
       m1 = std::max(m1, u); m2 = std::max(m2, v);
       sq += u * u + v * v;
     }
@@ -158,13 +166,13 @@ static void anneal_quarter(const Unit *const *lanes, int W, int *arr /* [8][W] a
   std::vector<int> cc(W);
   long total = 0;
   for (int k = 0; k < W; k++) { cc[k] = col_cost(k); total += cc[k]; }
-  std::vector<int> best(arr, arr + 8 * W);
+  std::vector<int> best(arr, arr + P * W);
   long best_total = total;
-  const int moves = effort * 220 * W + 400;
+  const int moves = effort * 28 * P * W + 400;
   double T = 10.0;
   const double decay = pow(0.05 / T, 1.0 / moves);
   for (int it = 0; it < moves; it++, T *= decay) {
-    const int i = rng.below(8), k1 = rng.below(W);
+    const int i = rng.below(P), k1 = rng.below(W);
     int k2 = rng.below(W - 1);
     if (k2 >= k1) k2++;
     const int j1 = arr[i * W + k1], j2 = arr[i * W + k2];
@@ -173,7 +181,7 @@ static void anneal_quarter(const Unit *const *lanes, int W, int *arr /* [8][W] a
     col_of(i, k1, x1, y1);
     col_of(i, k2, x2, y2);
     auto mv = [&](int k, int x, int y, int d) {
-      if (x >= 0) { c1[k * 8 + x] += d; c2[k * 8 + y] += d; }
+      if (x >= 0) { c1[k * P + x] += d; c2[k * P + y] += d; }
     };
     mv(k1, x1, y1, -1); mv(k2, x2, y2, -1); mv(k1, x2, y2, +1); mv(k2, x1, y1, +1);
     const int n1 = col_cost(k1), n2 = col_cost(k2);
@@ -182,7 +190,7 @@ static void anneal_quarter(const Unit *const *lanes, int W, int *arr /* [8][W] a
       arr[i * W + k1] = j2; arr[i * W + k2] = j1;
       cc[k1] = n1; cc[k2] = n2;
       total += delta;
-      if (total < best_total) { best_total = total; std::copy(arr, arr + 8 * W, best.begin()); }
+      if (total < best_total) { best_total = total; std::copy(arr, arr + P * W, best.begin()); }
     } else {
       mv(k1, x2, y2, -1); mv(k2, x1, y1, -1); mv(k1, x1, y1, +1); mv(k2, x2, y2, +1);
     }
@@ -193,7 +201,7 @@ static void anneal_quarter(const Unit *const *lanes, int W, int *arr /* [8][W] a
 // Order the arcs of the 32 units of a slice into columns.  `cols[k*32+lane]` = index into
 // lanes[lane]->arcs or -1 (idle).
 static void arrange_slice(const std::vector<const Unit *> &lanes, int width, std::vector<int> &cols, Rng &rng,
-                          int effort) {
+                          int effort, int P) {
   cols.assign((size_t)width * 32, -1);
   for (int l = 0; l < 32; l++) {
     if (!lanes[l]) continue;
@@ -202,24 +210,24 @@ static void arrange_slice(const std::vector<const Unit *> &lanes, int width, std
   }
   if (effort <= 0 || width < 2) return;
   static const Unit empty_unit{-1, {}};
-  std::vector<int> arr((size_t)8 * width);
-  for (int q = 0; q < 4; q++) {
-    const Unit *ql[8];
+  std::vector<int> arr((size_t)P * width);
+  for (int q = 0; q < 32 / P; q++) {
+    const Unit *ql[32];
     bool any = false;
-    for (int i = 0; i < 8; i++) {
-      ql[i] = lanes[q * 8 + i] ? lanes[q * 8 + i] : &empty_unit;
+    for (int i = 0; i < P; i++) {
+      ql[i] = lanes[q * P + i] ? lanes[q * P + i] : &empty_unit;
       any |= !ql[i]->arcs.empty();
-      for (int k = 0; k < width; k++) arr[(size_t)i * width + k] = cols[(size_t)k * 32 + q * 8 + i];
+      for (int k = 0; k < width; k++) arr[(size_t)i * width + k] = cols[(size_t)k * 32 + q * P + i];
     }
     if (!any) continue;
-    anneal_quarter(ql, width, arr.data(), rng, effort);
-    for (int i = 0; i < 8; i++)
-      for (int k = 0; k < width; k++) cols[(size_t)k * 32 + q * 8 + i] = arr[(size_t)i * width + k];
+    anneal_group(ql, P, width, arr.data(), rng, effort);
+    for (int i = 0; i < P; i++)
+      for (int k = 0; k < width; k++) cols[(size_t)k * 32 + q * P + i] = arr[(size_t)i * width + k];
   }
 }
 
 static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, const std::vector<uint32_t> &ab,
-                       const float *w, int n_a, int n_b, bool structure_only, bool log_domain, ViewBuild &v) {
+                       const float *w, int n_a, int n_b, bool structure_only, bool log_domain, int P, ViewBuild &v) {
   v.n_rows = n_rows;
   const int effort = pack_effort(K);
   Rng rng(0xC0FFEEull + (uint64_t)n_rows * 7919u + (uint64_t)K);
@@ -265,7 +273,7 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(),
                    [&](int x, int y) { return units[x].arcs.size() > units[y].arcs.size(); });
-  if (effort >= 1) balance_quarters(units, order);
+  if (effort >= 1) balance_groups(units, order, P);
   const int n_slices = ((int)units.size() + 31) / 32;
   v.n_slices = n_slices;
   v.rows.assign((size_t)n_slices * 32, -1);
@@ -286,7 +294,7 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
     }
     width = std::max(2, width + (width & 1));  // pairs; an empty slice still runs its epilogue
     std::vector<int> cols;
-    arrange_slice(lanes, width, cols, rng, structure_only ? 0 : effort);
+    arrange_slice(lanes, width, cols, rng, structure_only ? 0 : effort, P);
     width = (int)(cols.size() / 32);
     v.width[s] = width;
     s_ab[s].assign((size_t)width * 32, 0u);
@@ -308,24 +316,25 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
         ia[l] = rec & 0xffffu;
         ib[l] = rec >> 16;
       }
-      for (int q = 0; q < 4; q++) {
-        // idle lanes read element `g` of a bank group g nobody else uses in this quarter-column
+      for (int q = 0; q < 32 / P; q++) {
+        // idle lanes read element `g` of a bank group g nobody else uses in this phase of the column
+        const uint32_t mask = (uint32_t)P - 1u;
         unsigned used_a = 0, used_b = 0;
-        for (int i = 0; i < 8; i++)
-          if (s_ab[s][(size_t)k * 32 + q * 8 + i] != 0xffffffffu) { used_a |= 1u << (ia[q * 8 + i] & 7u); used_b |= 1u << (ib[q * 8 + i] & 7u); }
-        for (int i = 0; i < 8; i++) {
-          const size_t pos = (size_t)k * 32 + q * 8 + i;
+        for (int i = 0; i < P; i++)
+          if (s_ab[s][(size_t)k * 32 + q * P + i] != 0xffffffffu) { used_a |= 1u << (ia[q * P + i] & mask); used_b |= 1u << (ib[q * P + i] & mask); }
+        for (int i = 0; i < P; i++) {
+          const size_t pos = (size_t)k * 32 + q * P + i;
           if (s_ab[s][pos] != 0xffffffffu) continue;
           uint32_t ga = 0, gb = 0;
-          while (ga < 7 && ((used_a >> ga) & 1u)) ga++;
-          while (gb < 7 && ((used_b >> gb) & 1u)) gb++;
+          while (ga < mask && ((used_a >> ga) & 1u)) ga++;
+          while (gb < mask && ((used_b >> gb) & 1u)) gb++;
           used_a |= 1u << ga; used_b |= 1u << gb;
           if (ga >= na) ga = 0;
           if (gb >= nb) gb = 0;
           s_ab[s][pos] = ga | (gb << 16);
-          ia[q * 8 + i] = ga; ib[q * 8 + i] = gb;
+          ia[q * P + i] = ga; ib[q * P + i] = gb;
         }
-        const int wf = quarter_wavefronts(ia + 8 * q, 8) + quarter_wavefronts(ib + 8 * q, 8);
+        const int wf = phase_wavefronts(ia + P * q, P, P) + phase_wavefronts(ib + P * q, P, P);
         v.predicted += wf;
         slice_cost[s] += wf;
         v.ideal += 2;
@@ -388,7 +397,8 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
 
 int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, const int32_t *bt, const int32_t *bi,
                       const float *bp, const float *leaky, const float *init, const float *fin, int S, int K, int D,
-                      bool log_domain, void *out, int64_t out_bytes) {
+                      bool log_domain, int group_width, void *out, int64_t out_bytes) {
+  const int P = (group_width == 1) ? 32 : (group_width == 2 ? 16 : 8);  // lanes per phase of the vector gathers
   if (S <= 0 || K <= 0 || D <= 0 || !ft || !fi || !bt || !bi) return CHAIN_B200_ERR_INVALID_ARG;
   if (S > 65535 || D > 65535) return CHAIN_B200_ERR_UNSUPPORTED;
   if (log_domain && (S > 32767 || D > 32767)) return CHAIN_B200_ERR_UNSUPPORTED;  // bit 31 of the index word is the flag
@@ -424,14 +434,15 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
   }
   ViewBuild vb[3];
   const bool so = (out == nullptr);
-  build_view(S, Kv, row_dst, ab_fwd, bp, S, D, so, log_domain, vb[0]);
-  build_view(S, Kv, row_src, ab_bwd, fp, S, D, so, log_domain, vb[1]);
-  build_view(D, Kv, row_pdf, ab_gam, fp, S, S, so, log_domain, vb[2]);
+  build_view(S, Kv, row_dst, ab_fwd, bp, S, D, so, log_domain, P, vb[0]);
+  build_view(S, Kv, row_src, ab_bwd, fp, S, D, so, log_domain, P, vb[1]);
+  build_view(D, Kv, row_pdf, ab_gam, fp, S, S, so, log_domain, P, vb[2]);
 
   BlobHeader h;
   memset(&h, 0, sizeof(h));
   h.magic = kBlobMagic; h.version = kBlobVersion;
   h.S = S; h.K = Kv; h.D = D; h.nwarps = DEN_NW; h.log_domain = log_domain ? 1 : 0;
+  h.opt_G = 32 / P;
   h.S_pad = (S + 3) / 4 * 4; h.D_pad = (D + 3) / 4 * 4;
   size_t off = align_up(sizeof(BlobHeader));
   for (int i = 0; i < 3; i++) {
@@ -483,7 +494,7 @@ extern "C" {
 int64_t chain_b200_den_prepare_bytes(const int32_t *ft, const int32_t *fi, const int32_t *bt, const int32_t *bi, int S,
                                      int K, int D, unsigned flags) {
   return pack_den_blob(ft, fi, nullptr, bt, bi, nullptr, nullptr, nullptr, nullptr, S, K, D,
-                       (flags & CHAIN_B200_LOG_DOMAIN) != 0, nullptr, 0);
+                       (flags & CHAIN_B200_LOG_DOMAIN) != 0, (int)((flags >> 8) & 7u), nullptr, 0);
 }
 
 int chain_b200_den_prepare(const int32_t *ft, const int32_t *fi, const float *fp, const int32_t *bt,
@@ -491,7 +502,7 @@ int chain_b200_den_prepare(const int32_t *ft, const int32_t *fi, const float *fp
                            const float *fin, int S, int K, int D, unsigned flags, void *blob, int64_t blob_bytes) {
   if (!blob) return CHAIN_B200_ERR_INVALID_ARG;
   const int64_t r = pack_den_blob(ft, fi, fp, bt, bi, bp, leaky, init, fin, S, K, D,
-                                  (flags & CHAIN_B200_LOG_DOMAIN) != 0, blob, blob_bytes);
+                                  (flags & CHAIN_B200_LOG_DOMAIN) != 0, (int)((flags >> 8) & 7u), blob, blob_bytes);
   return r < 0 ? (int)r : CHAIN_B200_OK;
 }
 

@@ -24,6 +24,8 @@
 //    exp/clamp are applied while transposing them into the interleaved layout.
 //  * leaky-HMM mixing, per-frame renormalisation, total log-likelihood, the t=0 self-check
 //    and the zeroing of padded frames are all inside the one kernel.
+#include <cstring>
+
 #include "den_kernel_common.cuh"
 
 namespace chainb200 {
@@ -472,6 +474,17 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
 using namespace chainb200;
 
 extern "C" {
+
+int chain_b200_den_group_width(int S, int D, int B, int device) {
+  if (S <= 0 || D <= 0 || B <= 0) return 0;
+  BlobHeader h;
+  memset(&h, 0, sizeof(h));
+  h.S_pad = (S + 3) / 4 * 4; h.D_pad = (D + 3) / 4 * 4;
+  h.max_sub = 256;  // allowance for split rows, unknown before packing
+  int num_sms = 148;
+  if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) num_sms = 148;
+  return choose_G(h, B, num_sms);
+}
 
 size_t chain_b200_den_workspace_bytes(const void *blob_host, int B, int T) {
   const BlobHeader *h = (const BlobHeader *)blob_host;

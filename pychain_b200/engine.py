@@ -165,14 +165,18 @@ class PreparedDenGraph(object):
 _prepared_cache = OrderedDict()
 
 
-def prepare_den_graph(graph_tensors, num_states, D, device, log_domain=False):
+def prepare_den_graph(graph_tensors, num_states, D, device, log_domain=False, batch_size=None):
     """Pack (once; cached) a single graph given its reference-layout tensors (row 0 of each is
     used).  `graph_tensors` order = _GRAPH_NAMES_PROB, or _GRAPH_NAMES_LOG for a log-domain graph."""
     lib = _cabi.lib()
     names = _GRAPH_NAMES_LOG if log_domain else _GRAPH_NAMES_PROB
     rows = [t[0] if t.dim() == (3 if "transition" in n and "probs" not in n else 2) else t
             for t, n in zip(graph_tensors, names)]
-    key = (tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in rows), int(D), str(device), bool(log_domain))
+    # the record order is optimised for the group width the kernels will use for this batch size
+    dev_index = torch.device(device).index or 0
+    G = lib.chain_b200_den_group_width(int(num_states), int(D), int(batch_size), dev_index) if batch_size else 4
+    G = G if G in (1, 2, 4) else 4
+    key = (tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in rows), int(D), str(device), bool(log_domain), G)
     hit = _prepared_cache.get(key)
     if hit is not None:
         _prepared_cache.move_to_end(key)
@@ -184,7 +188,7 @@ def prepare_den_graph(graph_tensors, num_states, D, device, log_domain=False):
     else:
         ft, fi, fp, bt, bi, bp, lk, ini, fin = host
     S, K = int(num_states), int(ft.size(0))
-    pflags = _cabi.LOG_DOMAIN if log_domain else 0
+    pflags = (_cabi.LOG_DOMAIN if log_domain else 0) | (G << 8)
     nbytes = lib.chain_b200_den_prepare_bytes(_ptr(ft), _ptr(fi), _ptr(bt), _ptr(bi), S, K, int(D), pflags)
     if nbytes < 0:
         _cabi.check(int(nbytes), "chain_b200_den_prepare_bytes")
@@ -249,7 +253,7 @@ def forward_backward_prob(graph_tensors, x, lengths, num_states, leaky_coefficie
     path = path or DEN_PATH
     B = x.size(0)
     if path != "generic" and _is_shared(graph_tensors, B) and _shared_fits(int(num_states), int(x.size(2))):
-        prep = prepare_den_graph(graph_tensors, num_states, x.size(2), x.device)
+        prep = prepare_den_graph(graph_tensors, num_states, x.size(2), x.device, batch_size=B)
         return _run_den_shared(prep, x, lengths, leaky_coefficient, flags, stream=stream)
     return _run_generic(False, graph_tensors, x, lengths, num_states, leaky_coefficient, flags, stream=stream)
 
@@ -263,6 +267,6 @@ def forward_backward_log(graph_tensors, x, lengths, num_states, grad_as_log=True
     S, K = int(num_states), int(graph_tensors[0].size(1))
     if (path != "generic" and x.size(0) > 1 and _is_shared(graph_tensors, x.size(0)) and K >= 256
             and S <= 32767 and x.size(2) <= 32767 and _shared_fits(S, int(x.size(2)))):
-        prep = prepare_den_graph(graph_tensors, num_states, x.size(2), x.device, log_domain=True)
+        prep = prepare_den_graph(graph_tensors, num_states, x.size(2), x.device, log_domain=True, batch_size=x.size(0))
         return _run_den_shared(prep, x, lengths, 0.5, flags, stream=stream)
     return _run_generic(True, graph_tensors, x, lengths, num_states, 0.0, flags, stream=stream)

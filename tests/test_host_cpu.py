@@ -136,8 +136,8 @@ def test_graph_batch_layouts_and_reorder():
 
 def _parse_blob(blob):
     h = blob.numpy().tobytes()
-    magic, version, S, K, D, nw, S_pad, D_pad, max_sub, _ = struct.unpack_from("<II8i", h, 0)
-    views, off = [], 40
+    magic, version, S, K, D, nw, S_pad, D_pad, max_sub, _, opt_g, _, _, _ = struct.unpack_from("<II12i", h, 0)
+    views, off = [], 56
     for i in range(3):
         n_rows, n_slices, n_split, n_sub, n_recs, o_info, o_rows, o_recs, o_split = struct.unpack_from("<4i5q", h, off)
         off += 56
