@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg4")
-    ap.add_argument("--variant", default="uniform", choices=["uniform", "skew"])
+    ap.add_argument("--variant", default="uniform", choices=["uniform", "skew", "biphone"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

@@ -7,7 +7,9 @@ ships no data, tests or benchmark inputs, so every workload here is synthetic.
   s -> (s+1)%S guarantees every state has >=1 in- and out-arc and that the
   graph is strongly connected; the other K-S arcs are uniform (variant
   "skew": destination ~ Zipf, to model biphone in-degree skew); pdf uniform in
-  [0,D); arc / final log-weights make every state row-stochastic.
+  [0,D); arc / final log-weights make every state row-stochastic.  Variant
+  "biphone" has the structure of a real chain denominator instead (states =
+  phone pairs, the pdf of an arc is a function of its destination).
 * `linear_num_fst`  -- per-utterance numerator: left-to-right HMM, each phone
   = 2 states, self-loops + forward arcs, final only on the last state.
 * `make_inputs`     -- x = 2*randn(B,T,D) and descending lengths with max == T
@@ -39,9 +41,38 @@ def random_den_fst(S: int, K: int, D: int, seed: int = 0, variant: str = "unifor
         dst[S:] = (z - 1) % S
         perm = rng.permutation(S)  # so that the popular states are not 0,1,2,...
         dst[S:] = perm[dst[S:]]
+    elif variant == "biphone":
+        return _biphone_den_fst(S, K, D, rng)
     else:
         raise ValueError(variant)
     pdf = rng.integers(0, D, size=K)
+    out_deg = np.bincount(src, minlength=S)
+    logw = -np.log(out_deg[src] + 1.0)
+    fin = -np.log(out_deg + 1.0)
+    return Fst(S, 0, src, dst, pdf, logw.astype(np.float32), fin.astype(np.float32))
+
+
+def _biphone_den_fst(S, K, D, rng):
+    """A denominator graph with the structure of a biphone chain model (1-state HMMs, bigram-like
+    phone LM): state = (previous phone a, current phone b); it has a self loop (self-loop pdf of b
+    after a) and arcs to states (b, c) for a sparse set of successors c, all arcs ENTERING (b, c)
+    from another state carrying the same forward pdf of c after b.  Unlike the uniform variant the
+    pdf of an arc is a function of its destination, as in real chain graphs."""
+    P = max(2, int(np.floor(np.sqrt(S))))
+    n_states = P * P
+    fan = max(1, (K - n_states) // n_states)          # successors per state besides the self loop
+    succ = [rng.choice(P, size=min(fan, P), replace=False) for _ in range(P)]  # phone b -> next phones c
+    half = max(1, D // 2)
+    src, dst, pdf = [], [], []
+    for a in range(P):
+        for b in range(P):
+            st = a * P + b
+            src.append(st); dst.append(st); pdf.append(half + (a * 7919 + b * 104729) % (D - half))  # self loop
+            for c in succ[b]:
+                src.append(st); dst.append(b * P + int(c)); pdf.append((b * 31337 + int(c) * 613) % half)
+    for st in range(n_states, S):  # padding states up to S: unreachable, a self loop keeps them well formed
+        src.append(st); dst.append(st); pdf.append(st % D)
+    src, dst, pdf = np.asarray(src), np.asarray(dst), np.asarray(pdf)
     out_deg = np.bincount(src, minlength=S)
     logw = -np.log(out_deg[src] + 1.0)
     fin = -np.log(out_deg + 1.0)

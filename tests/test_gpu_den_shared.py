@@ -33,6 +33,7 @@ CASES = [
     dict(S=10, K=20, D=16, B=3, T=50, variable=True, coeff=0.1, initial_mode="leaky", final_mode="ones"),
     dict(S=37, K=300, D=19, B=5, T=33, variable=True, coeff=1e-5, variant="skew"),       # D % 4 != 0: non-TMA x path
     dict(S=301, K=1500, D=64, B=9, T=40, variable=True, coeff=1e-5),                     # S % 4 != 0
+    dict(S=1700, K=60000, D=120, B=5, T=12, variable=True, coeff=1e-5, variant="biphone"),  # structured, in-degree 35: split rows
 ]
 
 
