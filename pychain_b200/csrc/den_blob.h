@@ -18,7 +18,8 @@
 // plus kFifoPairs run-out pairs).  The row each lane owns in each slice comes from a
 // parallel per-warp stream of row codes, read one slice ahead.
 // Log-domain blobs (header.log_domain = 1; weights are log-probabilities, idle records carry -inf) keep
-// the end-of-slice flag in bit 31 of the index word instead (so S, D <= 32767) and are never split.
+// the end-of-slice flag in bit 31 of the index word instead (so S, D <= 32767); their sub-rows hand
+// over (max, sum-exp) pairs instead of plain partial sums.
 // Rows whose degree exceeds the view's cap are split into sub-rows; a sub-row writes its
 // partial sum to a scratch slot and the listed owner adds the slots up in order.
 #pragma once
@@ -27,7 +28,7 @@
 namespace chainb200 {
 
 constexpr uint32_t kBlobMagic = 0x42324348u;  // "HC2B"
-constexpr uint32_t kBlobVersion = 8;
+constexpr uint32_t kBlobVersion = 9;
 #ifndef CHAIN_B200_NW
 #define CHAIN_B200_NW 16
 #endif

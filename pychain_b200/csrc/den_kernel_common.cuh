@@ -125,7 +125,8 @@ inline DenWs den_ws_layout(const BlobHeader &h, int B, int T) {
 }
 
 inline size_t den_smem_bytes(const BlobHeader &h, int G) {
-  return sizeof(float) * ((size_t)2 * h.S_pad * G + (size_t)3 * h.D_pad * G + (size_t)h.max_sub * G) + 128;
+  return sizeof(float) * ((size_t)2 * h.S_pad * G + (size_t)3 * h.D_pad * G +
+                          (size_t)h.max_sub * G * (h.log_domain ? 2 : 1)) + 128;
 }
 
 // Relative cost of one frame for a group of G utterances (shared-memory wavefronts of

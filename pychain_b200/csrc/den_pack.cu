@@ -242,7 +242,6 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
   const double mean = (double)K / std::max(1, n_rows);
   int cap = std::max(32, 4 * (int)(mean + 0.999));
   cap += cap & 1;
-  if (log_domain) cap = 1 << 30;  // log-domain rows are never split
   std::vector<Unit> units;
   units.reserve(n_rows + 64);
   v.split.clear();

@@ -40,7 +40,8 @@ __device__ __forceinline__ void lse_rec(const uint32_t ab, const float w, const 
 // the index word.
 template <int G, bool L1C, class Epi>
 __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__restrict__ A,
-                                              const float *__restrict__ Bv, int warp, int lane, Epi &epi) {
+                                              const float *__restrict__ Bv, float *__restrict__ partial, int warp,
+                                              int lane, Epi &epi) {
   const uint2 *sp = v.recs + v.warp_info[3 * warp] + lane;
   const int npairs = (int)v.warp_info[3 * warp + 1];
   const int32_t *rp = v.rows + v.warp_info[3 * warp + 2] + lane;
@@ -65,6 +66,9 @@ __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__res
 #pragma unroll
         for (int g = 0; g < G; g++) o[g] = (m[g] > -INFINITY) ? m[g] + logf(s[g]) : -INFINITY;
         epi(row, o);
+      } else if (row <= -2) {  // piece of a split row: hand the (max, sum-exp) pairs to the owner
+        st_vec<G>(partial + (size_t)(-2 - row) * 2 * G, m);
+        st_vec<G>(partial + (size_t)(-2 - row) * 2 * G + G, s);
       }
 #pragma unroll
       for (int g = 0; g < G; g++) { m[g] = -INFINITY; s[g] = 0.f; }
@@ -113,6 +117,28 @@ __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__res
   }
 }
 
+// Rows that were split: merge the sub-rows' (max, sum-exp) pairs in fixed order and run the epilogue.
+template <int G, class Epi>
+__device__ __forceinline__ void fixup_split_log(const DView &v, const float *__restrict__ partial, Epi &epi) {
+  for (int i = threadIdx.x; i < v.n_split; i += DEN_NT) {
+    const int row = v.split[3 * i], first = v.split[3 * i + 1], cnt = v.split[3 * i + 2];
+    float m[G], s[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) { m[g] = -INFINITY; s[g] = 0.f; }
+    for (int j = 0; j < cnt; j++) {
+      float m2[G], s2[G];
+      ld_vec<G>(partial + (size_t)(first + j) * 2 * G, m2);
+      ld_vec<G>(partial + (size_t)(first + j) * 2 * G + G, s2);
+#pragma unroll
+      for (int g = 0; g < G; g++) lse_merge(m[g], s[g], m2[g], s2[g]);
+    }
+    float o[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) o[g] = (m[g] > -INFINITY) ? m[g] + logf(s[g]) : -INFINITY;
+    epi(row, o);
+  }
+}
+
 // log-sum-exp over the block of G per-thread (m, s) pairs; result to every thread.
 template <int G>
 __device__ __forceinline__ void block_lse_vec(float (&m)[G], float (&s)[G], float (&out)[G], float *red /* [DEN_NW*2*G] */) {
@@ -149,6 +175,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
   float *x_s = buf1 + (size_t)S_pad * G;
   float *xraw = x_s + (size_t)D_pad * G;
   float *gam_s = xraw + (size_t)D_pad * G;
+  float *partial = gam_s + (size_t)D_pad * G;  // [max_sub][2][G]
   const float *__restrict__ ini = p.init;
   const float *__restrict__ fin = p.fin;
   const bool clamp_x = (p.flags & CHAIN_B200_CLAMP_X) != 0;
@@ -273,7 +300,8 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
         }
         st_vec<G>(Bn + (size_t)row * G, a);
       };
-      sell_pass_log<G, L1C>(p.view[0], A, x_s, warp, lane, epi_fwd);
+      sell_pass_log<G, L1C>(p.view[0], A, x_s, partial, warp, lane, epi_fwd);
+      if (p.view[0].n_split) { __syncthreads(); fixup_split_log<G>(p.view[0], partial, epi_fwd); }
       float nsc[G];
       block_lse_vec<G>(pm, ps, nsc, red);  // contains the barrier that publishes alpha(t)
       float *awt = aws + (size_t)t * S_pad * G;
@@ -345,7 +373,8 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
         }
         st_vec<G>(gam_s + (size_t)row * G, out);
       };
-      sell_pass_log<G, L1C>(p.view[2], P, Q, warp, lane, epi_gam);
+      sell_pass_log<G, L1C>(p.view[2], P, Q, partial, warp, lane, epi_gam);
+      if (p.view[2].n_split) { __syncthreads(); fixup_split_log<G>(p.view[2], partial, epi_gam); }
       __syncthreads();  // gamma rows complete; everybody done reading P
 
       auto epi_bwd = [&](int row, const float (&o)[G]) {
@@ -354,7 +383,8 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
         for (int g = 0; g < G; g++) out[g] = (o[g] > -INFINITY && t < Lg[g]) ? o[g] - sct[g] : -INFINITY;
         st_vec<G>(P + (size_t)row * G, out);
       };
-      sell_pass_log<G, L1C>(p.view[1], Q, x_s, warp, lane, epi_bwd);
+      sell_pass_log<G, L1C>(p.view[1], Q, x_s, partial, warp, lane, epi_bwd);
+      if (p.view[1].n_split) { __syncthreads(); fixup_split_log<G>(p.view[1], partial, epi_bwd); }
       {  // this frame's gradient rows: one vector read per pdf, G coalesced row writes
         const float dead = as_log ? -INFINITY : 0.f;
         for (int n = tid; n < D; n += DEN_NT) {

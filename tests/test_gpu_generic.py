@@ -91,6 +91,29 @@ def test_num_generic_vs_oracle(cuda, B, T, D, variable):
         assert (rows[b, :int(lengths[b])] - 1).abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize("path", ["G1", "G4"])
+def test_log_domain_shared_graph_with_split_rows(cuda, path):
+    """A skewed graph (one state collects a large share of the arcs) through the log-domain shared
+    kernel: heavy rows are split and their (max, sum-exp) pairs merged."""
+    import os
+    fst = synth.random_den_fst(200, 3000, 24, seed=1003, variant="skew")
+    g = ChainGraph(fst, log_domain=True)
+    B, T, D = 5, 20, 24
+    gb = ChainGraphBatch(g, B)
+    x, lengths = synth.make_inputs(B, T, D, seed=10, variable=True)
+    x = x.clamp(-30, 30)
+    o_c, lp_c, lg_c, _, _ = co.num_c(gb, x, lengths)
+    gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_LOG)
+    os.environ["CHAIN_B200_G"] = path[1]
+    try:
+        r = engine.forward_backward_log(gt, x.to(cuda), lengths, gb.num_states, grad_as_log=False)
+    finally:
+        os.environ.pop("CHAIN_B200_G", None)
+    assert rel(r.objf.item(), o_c) < OBJF_RTOL
+    assert (r.grad.cpu() - lg_c.exp()).abs().max().item() < GRAD_ATOL
+    assert int(r.ok.item()) == 1
+
+
 @pytest.mark.parametrize("path", ["generic", "G1", "G2", "G4"])
 def test_log_domain_shared_graph(cuda, path):
     """BASELINE cfg2 flavour: a (leaky-free) denominator graph run through the log-domain entry,
