@@ -10,6 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the C-ABI library is a build product (git-ignored): make sure it exists and is current
+    # (nvcc cross-compiles sm_100a without a GPU; on the GPU box the prebuilt .so travels along)
+    try:
+        from pychain_b200 import build as _b
+        _b.build()
+    except Exception as e:  # leave the failure to the tests that need the library
+        print("pychain_b200.build failed:", e)
 
 
 @pytest.fixture(scope="session")
