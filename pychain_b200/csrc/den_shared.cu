@@ -30,14 +30,29 @@
 
 namespace chainb200 {
 
+// Blackwell packed fp32 math (SASS FMUL2 / FFMA2): two utterances per instruction, same rounding as
+// the scalar fmaf(a * w, b, acc).
+__device__ __forceinline__ void mul_fma_x2(float &acc0, float &acc1, float a0, float a1, float w, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rw, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rw, {%4, %4};\n\tmov.b64 rb, {%5, %6};\n\tmov.b64 rc, {%0, %1};\n\t"
+      "mul.rn.f32x2 ra, ra, rw;\n\tfma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(acc0), "+f"(acc1)
+      : "f"(a0), "f"(a1), "f"(w), "f"(b0), "f"(b1));
+}
+
 template <int G>
 __device__ __forceinline__ void consume_rec(const uint32_t ab, const float w, const float *__restrict__ A,
                                             const float *__restrict__ Bv, float (&acc)[G]) {
   float a[G], b[G];
   ld_vec<G>(A + (ab & 0xffffu) * G, a);
   ld_vec<G>(Bv + (ab >> 16) * G, b);
+  if constexpr (G % 2 == 0) {
 #pragma unroll
-  for (int g = 0; g < G; g++) acc[g] = fmaf(a[g] * w, b[g], acc[g]);
+    for (int g = 0; g < G; g += 2) mul_fma_x2(acc[g], acc[g + 1], a[g], a[g + 1], w, b[g], b[g + 1]);
+  } else {
+#pragma unroll
+    for (int g = 0; g < G; g++) acc[g] = fmaf(a[g] * w, b[g], acc[g]);
+  }
 }
 
 // One SELL pass: every lane owns one row (or sub-row) of each of its warp's slices and
