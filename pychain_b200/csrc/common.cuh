@@ -66,10 +66,12 @@ __device__ __forceinline__ float block_sum(float v, float *scratch) {
 // log(sum_i exp(v_i)) over the block from per-thread (m, s) pairs with
 // s = sum exp(v - m); m = -inf means "no terms".  Result to every thread.
 __device__ __forceinline__ void lse_merge(float &m, float &s, float m2, float s2) {
-  const float M = fmaxf(m, m2);
-  if (M == -INFINITY) { m = M; s = 0.f; return; }
-  s = s * expf(m - M) + s2 * expf(m2 - M);
-  m = M;
+  if (m2 > m) {  // one exponential per merge: the larger side keeps its scale
+    s = s * expf(m - m2) + s2;  // m = -inf: exp(-inf) = 0
+    m = m2;
+  } else if (m2 > -INFINITY) {
+    s += s2 * expf(m2 - m);
+  }
 }
 // Running log-sum-exp: fold one term into (m, s) with a single exp.
 __device__ __forceinline__ void lse_add(float &m, float &s, float t) {

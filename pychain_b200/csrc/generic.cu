@@ -136,6 +136,13 @@ __device__ __forceinline__ float load_x(const float *__restrict__ p, unsigned fl
 // GROWS: the three state rows and the frame live in global memory (L2) instead of shared memory --
 // the slow but complete path for graphs whose 3S+D floats exceed 227 KB (up to the 65535-state
 // limit the reference itself has, chain-computation.cc:126-127).
+__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <bool LOG, int GEN_NT, bool GROWS = false>
 __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericParams p) {
   extern __shared__ __align__(16) float smem[];
@@ -143,12 +150,8 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
   const int S = p.S, D = p.D, T = p.T, K = p.K;
   const int b = blockIdx.x, tid = threadIdx.x;
   const size_t gb = (p.flags & CHAIN_B200_GRAPH_SHARED) ? 0 : (size_t)b;
-  const int32_t *__restrict__ ft = p.ft + gb * K * 3;
   const int32_t *__restrict__ fi = p.fi + gb * S * 2;
-  const int32_t *__restrict__ bt = p.bt + gb * K * 3;
   const int32_t *__restrict__ bi = p.bi + gb * S * 2;
-  const float *__restrict__ fp = p.fp + gb * K;
-  const float *__restrict__ bp = p.bp + gb * K;
   const float *__restrict__ lk = LOG ? nullptr : p.leaky + gb * S;
   const float *__restrict__ ini = p.init + gb * S;
   const float *__restrict__ fin = p.fin + gb * S;
@@ -166,6 +169,23 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
 
   float *rows = GROWS ? p.rows_ws + (size_t)blockIdx.x * ((size_t)3 * S + D) : smem;
   float *bufA = rows, *bufB = rows + S, *bufC = rows + 2 * S, *x_s = rows + 3 * S;
+  // Log-domain rows in shared memory: the next frame of x (and, in the backward pass, the next
+  // alpha row) is fetched by cp.async while the current frame is processed; the clamp is applied
+  // when an element is used.  Layout: 4 state rows + 2 frames.
+  constexpr bool PF = LOG && !GROWS;
+  float *bufD = rows + 3 * S;
+  float *xb[2] = {rows + 4 * S, rows + 4 * S + D};
+  const bool clamp_use = PF && (p.flags & CHAIN_B200_CLAMP_X);
+  auto XV = [&](int n) { return clamp_use ? clampf(x_s[n], kClampLo, kClampHi) : x_s[n]; };
+  auto issue_frame = [&](int f, const float *arow, float *adst) {  // x frame f (+ optionally one alpha row)
+    const float *xr = x + (size_t)f * D;
+    float *dst = xb[f & 1];
+    for (int n = tid; n < D; n += GEN_NT) cp_async4(dst + n, xr + n);
+    if (arow)
+      for (int i = tid; i < S; i += GEN_NT) cp_async4(adst + i, arow + i);
+    cp_async_commit();
+  };
+  if (PF && L > 0) issue_frame(0, nullptr, nullptr);
   double logp = 0.0;  // only thread 0's copy is used
 
   // ------------------------------------------------------------ forward, t = 0
@@ -191,9 +211,16 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
 
   // ------------------------------------------------------------ forward, t = 1..L
   for (int t = 1; t <= L; t++) {
-    const float *xr = x + (size_t)(t - 1) * D;
-    for (int n = tid; n < D; n += GEN_NT) x_s[n] = load_x(xr + n, p.flags, LOG);
-    __syncthreads();
+    if (PF) {
+      cp_async_wait_all();
+      __syncthreads();  // frame t-1 has landed; the other frame buffer is free
+      if (t < L) issue_frame(t, nullptr, nullptr);
+      x_s = xb[(t - 1) & 1];
+    } else {
+      const float *xr = x + (size_t)(t - 1) * D;
+      for (int n = tid; n < D; n += GEN_NT) x_s[n] = load_x(xr + n, p.flags, LOG);
+      __syncthreads();
+    }
     float tot;
     if (!LOG) {
       const float inv = 1.0f / tot_prev;
@@ -226,7 +253,7 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
         float m = -INFINITY, sm = 0.f;
         for (int k = k0; k < k1; k++) {
           const uint2 r = __ldg(&brec[k]);
-          lse_add(m, sm, bufA[r.x & 0xffffu] + __uint_as_float(r.y) + x_s[r.x >> 16]);
+          lse_add(m, sm, bufA[r.x & 0xffffu] + __uint_as_float(r.y) + XV(r.x >> 16));
         }
         const float a = (m > -INFINITY) ? m + logf(sm) - tot_prev : -INFINITY;
         bufB[h] = a;
@@ -265,15 +292,26 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
   }
   if (tid == 0 && p.logp) p.logp[b] = (float)logp;
   __syncthreads();
+  if (PF && L > 0) {  // frame L-1 of x is still in xb[(L-1)&1]; fetch alpha(L-1) into bufA
+    for (int i = tid; i < S; i += GEN_NT) cp_async4(bufA + i, alpha_ws + (size_t)(L - 1) * S + i);
+    cp_async_commit();
+  }
 
   // ------------------------------------------------------------ backward, t = L-1..0
   for (int t = L - 1; t >= 0; t--) {
-    const float *xr = x + (size_t)t * D;
-    const float *aw = alpha_ws + (size_t)t * S;
-    for (int n = tid; n < D; n += GEN_NT) x_s[n] = load_x(xr + n, p.flags, LOG);
-    for (int i = tid; i < S; i += GEN_NT) bufA[i] = aw[i];
     const float tot_t = tot_ws[t];
-    __syncthreads();
+    if (PF) {
+      cp_async_wait_all();
+      __syncthreads();  // x(t) and alpha(t) have landed; bufD and the other frame buffer are free
+      if (t > 0) issue_frame(t - 1, alpha_ws + (size_t)(t - 1) * S, bufD);
+      x_s = xb[t & 1];
+    } else {
+      const float *xr = x + (size_t)t * D;
+      const float *aw = alpha_ws + (size_t)t * S;
+      for (int n = tid; n < D; n += GEN_NT) x_s[n] = load_x(xr + n, p.flags, LOG);
+      for (int i = tid; i < S; i += GEN_NT) bufA[i] = aw[i];
+      __syncthreads();
+    }
     float *gr = grad + (size_t)t * D;
     float gsum = 0.f;
     if (!LOG) {
@@ -316,7 +354,7 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
     } else {
       for (int n = tid; n < D; n += GEN_NT) {
         const int j0 = pptr[n], j1 = pptr[n + 1];
-        const float xn = x_s[n] - tot_t;
+        const float xn = XV(n) - tot_t;
         float m = -INFINITY, sm = 0.f;
         for (int j = j0; j < j1; j++) {
           const uint2 r = __ldg(&prec[j]);
@@ -335,7 +373,7 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
         float m = -INFINITY, sm = 0.f;
         for (int k = k0; k < k1; k++) {
           const uint2 r = __ldg(&frec[k]);
-          lse_add(m, sm, __uint_as_float(r.y) + bufB[r.x & 0xffffu] + x_s[r.x >> 16] - tot_t);
+          lse_add(m, sm, __uint_as_float(r.y) + bufB[r.x & 0xffffu] + XV(r.x >> 16) - tot_t);
         }
         const float v = (m > -INFINITY) ? m + logf(sm) : -INFINITY;
         bufC[h] = v;
@@ -346,6 +384,7 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
       }
     }
     float *tmp = bufB; bufB = bufC; bufC = tmp;
+    if (PF) { tmp = bufA; bufA = bufD; bufD = tmp; }  // the prefetched alpha(t-1)
     __syncthreads();
   }
   if (L == 0 && p.diag && tid == 0) { p.diag[2 * b] = 1.f; p.diag[2 * b + 1] = 1.f; }
@@ -402,7 +441,12 @@ struct GenericWs {
   size_t alpha, tot, pdf_ptr, pdf_rec, bwd_rec, fwd_rec, logp, diag, rows, total;
 };
 
-static bool generic_rows_in_global(int S, int D) { return sizeof(float) * ((size_t)3 * S + D) > 227 * 1024 - 1024; }
+static size_t generic_smem_bytes(int S, int D, bool log_domain) {
+  return sizeof(float) * (log_domain ? (size_t)4 * S + 2 * (size_t)D : (size_t)3 * S + D);
+}
+static bool generic_rows_in_global(int S, int D, bool log_domain = true) {  // default: the larger (log) footprint
+  return generic_smem_bytes(S, D, log_domain) > 227 * 1024 - 1024;
+}
 
 static GenericWs generic_ws_layout(int B, int T, int D, int S, int K, unsigned flags) {
   GenericWs w;
@@ -437,8 +481,9 @@ static int run_generic(const int32_t *ft, const int32_t *fi, const float *fp, co
   if (S > 65535 || D > 65535) return CHAIN_B200_ERR_UNSUPPORTED;
   const GenericWs w = generic_ws_layout(B, T, D, S, K, flags);
   if (!ws || ws_bytes < w.total) return CHAIN_B200_ERR_WORKSPACE;
-  const bool grows = generic_rows_in_global(S, D);
-  const size_t smem = grows ? 0 : sizeof(float) * ((size_t)3 * S + D);
+  const bool grows = generic_rows_in_global(S, D, LOG);
+  // log domain: 4 state rows + 2 frames (cp.async prefetch); probability domain: 3 rows + 1 frame
+  const size_t smem = grows ? 0 : generic_smem_bytes(S, D, LOG);
   const size_t sort_smem = sizeof(int) * (size_t)(D + 1);
   if (sort_smem > 227 * 1024 - 1024) return CHAIN_B200_ERR_UNSUPPORTED;
 
