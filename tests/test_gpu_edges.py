@@ -143,3 +143,34 @@ def test_ok_flag_and_verbose_report(cuda, capfd):
         gt = tuple(getattr(gs, n) for n in engine._GRAPH_NAMES_PROB)
         r = engine.forward_backward_prob(gt, bad.to(cuda), lengths, gs.num_states, 1e-5, x_is_exp=False, clamp=True, path=path)
         assert int(r.ok.item()) == 0
+
+
+def test_cuda_graph_capture(cuda):
+    """Every C-ABI call is asynchronous and allocation-free, so a forward-backward can be captured in
+    a CUDA graph and replayed (inputs already on the device; outputs live in the graph's pool)."""
+    g = ChainGraph(synth.random_den_fst(120, 700, 32, seed=4))
+    B, T, D = 6, 25, 32
+    x, lengths = synth.make_inputs(B, T, D, seed=5, variable=True)
+    gb = ChainGraphBatch(g, B).to(cuda)
+    gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_PROB)
+    xd, ld = x.to(cuda), lengths.to(cuda)
+    eager = engine.forward_backward_prob(gt, xd, ld, gb.num_states, 1e-5, x_is_exp=False, clamp=True)
+    torch.cuda.synchronize()
+    static_x = xd.clone()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        engine.forward_backward_prob(gt, static_x, ld, gb.num_states, 1e-5, x_is_exp=False, clamp=True)  # warm-up: packs, caches
+    torch.cuda.current_stream().wait_stream(side)
+    with torch.cuda.graph(graph):
+        r = engine.forward_backward_prob(gt, static_x, ld, gb.num_states, 1e-5, x_is_exp=False, clamp=True)
+    static_x.copy_(xd * 0.5)
+    graph.replay()
+    torch.cuda.synchronize()
+    want = engine.forward_backward_prob(gt, xd * 0.5, ld, gb.num_states, 1e-5, x_is_exp=False, clamp=True)
+    assert torch.equal(r.objf, want.objf) and torch.equal(r.grad, want.grad)
+    static_x.copy_(xd)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(r.objf, eager.objf) and torch.equal(r.grad, eager.grad)
