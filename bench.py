@@ -45,6 +45,11 @@ def parse():
     ap.add_argument("--variant", default="uniform", choices=["uniform", "skew", "biphone"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA path")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the live ncu measurement of DRAM traffic")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the config's batch per GPU; strong: the config's GLOBAL batch split over the GPUs")
+    ap.add_argument("--probe", action="store_true", help=argparse.SUPPRESS)
     return ap.parse_args()
 
 
@@ -100,16 +105,6 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------ workload
-def make_workload(cfg, variant, rank):
-    import torch
-    from pychain_b200 import synth, ChainGraphBatch
-    c = synth.CONFIGS[cfg]
-    graph = synth.den_graph_for(cfg, variant=variant)
-    x, lengths = synth.make_inputs(c["B"], c["T"], c["D"], seed=2000 + int(cfg[3:]) + 7919 * rank, variable=c["variable"])
-    return c, graph, x, lengths
-
-
-# ------------------------------------------------------------------ reference CPU arm / cpu_baseline
 def mode_of(cfg):
     """cfg2 is the leaky-free denominator through the LOG-domain entry (BASELINE.json configs[1]),
     cfg3 the full ChainLoss (numerator + denominator, forward + backward); the rest are the
@@ -117,96 +112,129 @@ def mode_of(cfg):
     return {"cfg2": "logden", "cfg3": "loss"}.get(cfg, "den")
 
 
-def _ref_worker(args):
-    """One host process: the reference extension's CPU path on a shard."""
-    cfg, variant, start, count, reps = args
-    import torch
-    torch.set_num_threads(1)
-    from pychain_b200 import synth, ChainGraph, ChainGraphBatch
-    from oracle import chain_oracle as co
-    c = synth.CONFIGS[cfg]
-    mode = mode_of(cfg)
-    x, _ = synth.make_inputs(count, c["T"], c["D"], seed=4000 + start)
-    lengths = torch.full((count,), c["T"], dtype=torch.long)
-    xc = x.clamp(-30, 30)
-    use_ref = co.ref_available()
-    if mode == "logden":
-        lg = ChainGraph(synth.random_den_fst(c["S"], c["K"], c["D"], seed=1002), log_domain=True)
-        lgb = ChainGraphBatch(lg, count).materialize()
-    else:
-        graph = synth.den_graph_for(cfg, variant=variant)
-        gb = ChainGraphBatch(graph, count).materialize()
-        ex = xc.exp()
-    if mode == "loss":
-        nb = synth.make_num_batch(count, c["T"], c["D"], seed=52 + start)
-    out = []
-    objf = 0.0
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        if mode == "logden":
-            o = co.num_ref(lgb, xc, lengths)[0] if use_ref else co.num_c(lgb, xc, lengths)[0]
-            objf = float(o)
-        else:
-            o = co.den_ref(gb, ex, lengths, 1e-5)[0] if use_ref else co.den_c(gb, ex, lengths, 1e-5)[0]
-            objf = float(o)
-            if mode == "loss":
-                o2 = co.num_ref(nb, xc, lengths)[0] if use_ref else co.num_c(nb, xc, lengths)[0]
-                objf -= float(o2)
-        out.append(time.perf_counter() - t0)
-    return out, objf, "reference" if use_ref else "port"
+def workload_name(cfg, variant, c):
+    what = {"den": "den fwd+bwd, leaky=1e-5", "logden": "leaky-free den fwd+bwd through the log-domain entry",
+            "loss": "full ChainLoss (per-utterance numerators + den, leaky=1e-5) fwd+bwd, variable T"}[mode_of(cfg)]
+    return "%s: %s, S=%d states K=%d arcs (%s synthetic FST), B=%d/GPU T=%d D=%d" % (
+        cfg, what, c["S"], c["K"], variant, c["B"], c["T"], c["D"])
 
 
-def cpu_reference_run(cfg, variant, sample, reps, max_workers=None):
-    """Time `reps` passes of the reference CPU path over `sample` utterances
-    sharded over host processes (its arc loops are single-threaded, so
-    processes are the only way it can use more than one core).  Returns
-    (list of wall seconds per pass, workers, kind, objf)."""
-    import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    workers = max(1, min(cores, sample, max_workers or 64))
-    per = [sample // workers + (1 if i < sample % workers else 0) for i in range(workers)]
-    starts = [sum(per[:i]) for i in range(workers)]
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(workers) as pool:
-        res = pool.map(_ref_worker, [(cfg, variant, s, n, reps + 1) for s, n in zip(starts, per) if n > 0])
-    kind = res[0][2]
-    # pass i takes as long as its slowest worker; drop the first (cold) pass
-    walls = [max(r[0][i] for r in res) for i in range(1, reps + 1)]
-    return walls, len(res), kind, sum(r[1] for r in res)
+def config_dict(a, spec, world):
+    """ONE definition of `config` for both arms (the driver compares them key by key)."""
+    B, T, D, S = spec["B"], spec["T"], spec["D"], spec["S"]
+    return {"workload": workload_name(a.config, a.variant, spec), "global_batch": B * world,
+            "frames_per_step": frames_of(spec) * world,
+            "scaling": a.scaling,
+            "parallelism": "batch-shard x%d, one NCCL sum of {objf,frames,ok}" % world,
+            "l2": "inputs (%.0f MB x + %.0f MB alpha spill per step) exceed the 126 MB L2; no flush needed" % (
+                B * T * D * 4 / 1e6, B * (T + 1) * S * 4 / 1e6)}
+
+
+def frames_of(spec):
+    from pychain_b200 import synth
+    return int(synth.make_lengths(spec["B"], spec["T"], spec["x_seed"], spec["variable"]).sum())
+
+
+def make_spec(a, rank, world):
+    from pychain_b200 import synth
+    spec = synth.workload_spec(a.config, a.variant, rank)
+    if a.scaling == "strong":   # the global batch of the config is fixed and split over the ranks (cfg5: 4096)
+        gb = synth.CONFIGS[a.config].get("B_global", spec["B"])
+        spec["B"] = gb // world
+    return spec
+
+
+def median(v):
+    v = sorted(v)
+    n = len(v)
+    return v[n // 2] if n % 2 else 0.5 * (v[n // 2 - 1] + v[n // 2])
+
+
+# ------------------------------------------------------------------ reference CPU path (the arm and the cpu_baseline leg)
+def cpu_sample_size(spec, seconds_per_pass, explicit=0):
+    """Utterances per pass: the whole batch when the box's cores finish it in about `seconds_per_pass`
+    (BASELINE.md cost model: 2*K*T / 3.4e8 s per utterance and core; 3.0e7 in the log domain)."""
+    per_seq_s = 2.0 * spec["K"] * spec["T"] / (3.0e7 if spec["mode"] == "logden" else 3.4e8)
+    cores = min(os.cpu_count() or 1, 64)
+    n = explicit or max(cores, min(spec["B"], int(cores * seconds_per_pass / per_seq_s) or 1))
+    return min(n, spec["B"])
+
+
+def cpu_reference(spec, sample, passes, grad_for=()):
+    """`passes` timed passes (+1 cold pass, dropped) of the reference's CPU path over utterances
+    [0, sample) of the workload, one host process per shard.  ONE estimator for both legs: the median
+    pass, each pass as long as its slowest process."""
+    from oracle import ref_parallel as rp
+    r = rp.run(spec, sample=sample, reps=passes, grad_for=grad_for, drop_first=True)
+    r["seconds"] = median(r["walls"])
+    r["value"] = r["frames"] / r["seconds"]
+    r["desc"] = "%d of %d utterances (%d frames) per pass, median of %d passes after 1 cold pass, %d host processes" % (
+        r["sample"], spec["B"], r["frames"], passes, r["workers"])
+    return r
 
 
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    from pychain_b200 import synth
-    c = synth.CONFIGS[a.config]
-    per_seq_s = 2.0 * c["K"] * c["T"] / (3.0e7 if mode_of(a.config) == "logden" else 3.4e8)  # BASELINE.md cost model, one core
-    cores = min(os.cpu_count() or 1, 64)
-    sample = a.cpu_sample or max(cores, min(c["B"], int(cores * 2.0 / per_seq_s) or 1))
-    sample = min(sample, c["B"])
-    walls, workers, kind, _ = cpu_reference_run(a.config, a.variant, sample, max(1, a.steps))
-    frames = sample * c["T"]
-    mean = sum(walls) / len(walls)
-    val = frames / mean
+    spec = make_spec(a, 0, world)
+    sample = cpu_sample_size(spec, 2.0, a.cpu_sample)
+    passes, W = max(1, a.steps), max(3, a.warmup)
+    r = cpu_reference(spec, sample, passes + W - 1)   # W warm-up passes: 1 cold (dropped inside) + W-1 dropped here
+    walls = r["walls"][W - 1:]
+    sec = median(walls)
+    val = r["frames"] / sec
+    r["desc"] = "%d of %d utterances (%d frames) per step, median of %d steps after %d warm-up passes, %d host processes" % (
+        r["sample"], spec["B"], r["frames"], len(walls), W, r["workers"])
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": len(walls),
-        "warmup": 1, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a.config, a.variant, c), "sample_utterances_per_step": sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": workers, "kind": kind,
-                         "sample": "%d of %d utterances x T=%d per step, %d host processes" % (sample, c["B"], c["T"], workers)},
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": W, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_dict(a, spec, world),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": r["workers"], "kind": r["kind"], "sample": r["desc"]},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "objf": r["objf"] - (r["objf_num"] or 0.0) if spec["mode"] == "loss" else r["objf"],
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_name(cfg, variant, c):
-    what = {"den": "den fwd+bwd, leaky=1e-5", "logden": "leaky-free den fwd+bwd through the log-domain entry",
-            "loss": "full ChainLoss (per-utterance numerators + den, leaky=1e-5) fwd+bwd, variable T"}[mode_of(cfg)]
-    return "%s: %s, S=%d states K=%d arcs (%s random FST), B=%d/GPU T=%d D=%d" % (
-        cfg, what, c["S"], c["K"], variant, c["B"], c["T"], c["D"])
+# ------------------------------------------------------------------ DRAM traffic of the dominant kernel, measured live
+def measure_traffic(a, kernel_regex):
+    """`dram__bytes_read.sum + dram__bytes_write.sum` of ONE launch of the dominant kernel, from an ncu run
+    of this same script (probe mode: warm-up launches only, nothing printed).  None if ncu cannot run."""
+    import shutil
+    import tempfile
+    ncu = shutil.which("ncu")
+    if not ncu:
+        return None, "ncu not found"
+    with tempfile.NamedTemporaryFile(suffix=".csv", delete=False) as f:
+        log = f.name
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none",
+           "-k", "regex:" + kernel_regex, "-s", "1", "-c", "1", "--csv", "--log-file", log,
+           sys.executable, os.path.abspath(__file__), "--probe", "--config", a.config, "--variant", a.variant,
+           "--scaling", a.scaling]
+    try:
+        subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=240,
+                       env=dict(os.environ, WORLD_SIZE="1", RANK="0", LOCAL_RANK=os.environ.get("LOCAL_RANK", "0")))
+        import csv
+        total, unit_scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rows = [r for r in csv.reader(open(log)) if len(r) > 3]
+        head = next(r for r in rows if "Metric Name" in r)
+        iname, iunit, ival = head.index("Metric Name"), head.index("Metric Unit"), head.index("Metric Value")
+        n = 0
+        for r in rows:
+            if len(r) > ival and r[iname] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(r[ival].replace(",", "")) * unit_scale.get(r[iunit], 1.0)
+                n += 1
+        return (total if n == 2 else None), ("ncu --metrics dram__bytes_{read,write}.sum -k regex:%s -c 1, same command, this run" % kernel_regex)
+    except Exception as ex:
+        return None, "ncu probe failed: %r" % (ex,)
+    finally:
+        try:
+            os.unlink(log)
+        except OSError:
+            pass
 
 
 # ------------------------------------------------------------------ main arm
@@ -217,7 +245,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from pychain_b200 import synth, engine, ChainGraphBatch, ChainFunction
+    from pychain_b200 import synth, engine, ChainGraphBatch, ChainFunction, ChainLoss
+    from pychain_b200 import distributed as pdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -232,39 +261,37 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
-    c, graph, x_host, lengths = make_workload(a.config, a.variant, rank)
-    B, T, D, S, K = c["B"], c["T"], c["D"], c["S"], c["K"]
-    mode = mode_of(a.config)
-    from pychain_b200 import ChainGraph, ChainLoss
-    if mode == "logden":
-        graph = ChainGraph(synth.random_den_fst(S, K, D, seed=1002), log_domain=True)
+    spec = make_spec(a, rank, world)
+    graph, num_batch, x_host, lengths = synth.build_workload(spec)
+    B, T, D, S, K = spec["B"], spec["T"], spec["D"], spec["S"], spec["K"]
+    mode = spec["mode"]
     gb = ChainGraphBatch(graph, B)
     gt = tuple(getattr(gb, n) for n in (engine._GRAPH_NAMES_LOG if mode == "logden" else engine._GRAPH_NAMES_PROB))
     x_dev = x_host.to(dev)
-    x_pin = x_host.pin_memory()
     frames = int(lengths.sum())
-    stats = torch.zeros(3, dtype=torch.float32, device=dev)
     if mode == "loss":
-        num_batch = synth.make_num_batch(B, T, D, seed=52 + 1000 * rank)
         crit = ChainLoss(graph, 1e-5, avg=False)
-        kernel_name = "den_shared_kernel + chain_generic_kernel<log>"
+        kernel_name, kernel_regex = "den_shared_kernel + chain_generic_kernel<log>", None
     else:
         kernel_name = "den_shared_log_kernel" if mode == "logden" else "den_shared_kernel"
+        kernel_regex = "den_shared"
 
     class _R(object):
         pass
 
-    def run_engine(xt):
+    def run_engine(xt, nb=None, ln=None, g=None):
         """One step on a device-resident input; returns an object with .objf and .ok (device tensors)."""
+        ln = lengths if ln is None else ln
+        g = gt if g is None else g
         if mode == "den":
-            return engine.forward_backward_prob(gt, xt, lengths, S, 1e-5, x_is_exp=False, clamp=True)
+            return engine.forward_backward_prob(g, xt, ln, S, 1e-5, x_is_exp=False, clamp=True)
         if mode == "logden":
-            return engine.forward_backward_log(gt, xt, lengths, S, grad_as_log=False, clamp=True)
+            return engine.forward_backward_log(g, xt, ln, S, grad_as_log=False, clamp=True)
         xg = xt.detach().requires_grad_(True)
-        loss = crit(xg, lengths, num_batch)
+        loss = crit(xg, ln, num_batch if nb is None else nb)
         loss.backward()
         r = _R()
-        r.objf, r.ok = loss.detach(), ChainFunction.last_ok
+        r.objf, r.ok, r.grad, r.stats = loss.detach(), ChainFunction.last_ok, xg.grad, None
         return r
 
     def run_api(xt):
@@ -273,14 +300,14 @@ def main():
             return run_engine(xt).objf
         return ChainFunction.apply(xt, lengths, gb, 1e-5) if mode == "den" else ChainFunction.apply(xt, lengths, gb)
 
-    def step_resident():
-        r = run_engine(x_dev)
-        if world > 1:  # the single collective of the sharded loss: sum of {objf, frames, not ok}
-            stats[0] = r.objf
-            stats[1] = float(frames)
-            stats[2] = (1 - r.ok[0]).float()
-            dist.all_reduce(stats)
-        return r
+    def reduce_step(r):
+        """The single collective of the sharded loss: sum of {objf, frames, not ok} (finalize_kernel leaves the
+        three numbers in one buffer: no extra launch, no host-to-device scalar)."""
+        if world > 1:
+            if getattr(r, "stats", None) is not None:
+                return pdist.reduce_result(r)
+            return pdist.reduce_stats(r.objf, frames, r.ok)
+        return None
 
     def barrier():
         if world > 1:
@@ -289,8 +316,11 @@ def main():
 
     # -------- warm-up (also packs the graph once; not part of a step)
     for _ in range(max(3, a.warmup)):
-        r = step_resident()
+        r = run_engine(x_dev)
+        reduce_step(r)
     barrier()
+    if a.probe:   # measure_traffic's child: the profiled launch is one of the warm-up launches
+        return
     launches0 = engine.launch_count()
 
     # -------- timed: K steps, inputs resident, CUDA events, max over ranks
@@ -305,11 +335,7 @@ def main():
         kern_ev[i][0].record()
         r = run_engine(x_dev)
         kern_ev[i][1].record()
-        if world > 1:
-            stats[0] = r.objf
-            stats[1] = float(frames)
-            stats[2] = (1 - r.ok[0]).float()
-            dist.all_reduce(stats)
+        red = reduce_step(r)
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -321,13 +347,20 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, kern_ms = float(t[0]), float(t[1])
     ms_step = ms_total / a.steps
-    value = frames * world / (ms_step * 1e-3)
+    frames_global = frames
+    if world > 1:
+        ft = torch.tensor([float(frames)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ft)
+        frames_global = int(ft[0])
+    value = frames_global / (ms_step * 1e-3)
     objf = float(r.objf)
+    objf_global = float(red[0]) if red is not None else objf
     ok = int(r.ok.item())
 
     # -------- e2e: public API, pinned host input -> H2D, objf -> D2H, every step.
     # The H2D copy of step i+1 is issued on a copy stream while step i computes (two staging
     # buffers), as a training loop's prefetcher would; every step's copy is inside the timed region.
+    x_pin = x_host.pin_memory()
     stage = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     copy_stream = torch.cuda.Stream(device=dev)
@@ -347,11 +380,7 @@ def main():
             main_stream.wait_event(ready[i % 2])
             o = run_api(stage[i % 2])
             if world > 1:
-                stats[0] = o
-                stats[1] = float(frames)
-                stats[2] = 0.0
-                dist.all_reduce(stats)
-                last = stats[0].item()
+                last = pdist.reduce_stats(o, frames, True)[0].item()
             else:
                 last = o.item()  # D2H of the step's result
         return last
@@ -362,11 +391,21 @@ def main():
     run_e2e(a.steps)
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    # the PCIe ceiling of e2e: the H2D copy of one step's input alone
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for _ in range(3):
+        stage[0].copy_(x_pin, non_blocking=True)
+    h1.record()
+    torch.cuda.synchronize()
+    h2d_ms = h0.elapsed_time(h1) / 3
+    t = torch.tensor([e0.elapsed_time(e1), h2d_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t[0]) / a.steps
-    e2e_val = frames * world / (e2e_ms * 1e-3)
+    h2d_ms = float(t[1])
+    e2e_val = frames_global / (e2e_ms * 1e-3)
+    del stage
 
     if rank != 0:
         if world > 1:
@@ -379,66 +418,135 @@ def main():
     if os.path.isfile(peaks_path):
         try:
             peak = float(json.load(open(peaks_path))["hbm_gbs"])
-            peak_src = "MEASURED_PEAKS.json hbm_gbs"
+            peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)"
         except Exception:
             pass
     alg_bytes = frames * (12.0 * D + 8.0 * S)
+    ro_bytes = frames * (8.0 * D + 4.0 * S)
     if mode == "loss":
         alg_bytes += frames * (12.0 * D + 8.0 * num_batch.num_states)
+        ro_bytes += frames * (8.0 * D + 4.0 * num_batch.num_states)
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.isfile(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(a.config + ":" + a.variant)
-        except Exception:
-            traffic = None
+    traffic, traffic_src = None, "not measured"
+    if kernel_regex and world == 1 and not a.no_traffic:
+        traffic, traffic_src = measure_traffic(a, kernel_regex)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": kernel_name, "kernel_ms": kern_ms,
-                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "note": "algorithmic bytes = F*(12D+8S) (x2 for the full loss: numerator + denominator); the kernels are shared-memory-gather / latency bound, see DESIGN.md"}
+                "traffic": traffic, "traffic_source": traffic_src,
+                "read_only_achieved": ro_bytes / (kern_ms * 1e-3) / 1e9,
+                "read_only_frac": ro_bytes / (kern_ms * 1e-3) / 1e9 / peak,
+                "kernel": kernel_name, "kernel_ms": kern_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "read_only_bytes_per_launch": ro_bytes, "peak_source": peak_src,
+                "note": "algorithmic bytes = F*(12D+8S): x read in the alpha and the beta pass, grad written, alpha row "
+                        "written + read (x2 for the full loss); read-only = F*(8D+4S) (north_star's 'HBM-read roofline'); "
+                        "the kernels are shared-memory-gather bound, see DESIGN.md"}
 
-    # secondary ceiling: the kernels gather 6 fp32 operands per arc and valid frame from
-    # shared memory (alpha/x, beta/x, alpha/beta); peak = SMs x 128 B/clk x SM clock
+    # secondary ceiling: the L1 / shared-memory data pipe, 128 B/clk/SM
     sm_clock = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
     smem_peak = torch.cuda.get_device_properties(dev).multi_processor_count * 128.0 * sm_clock / 1e9
     gather_bytes = 24.0 * K * frames
-    roofline["secondary"] = {"bound": "shared-memory gathers", "achieved": gather_bytes / (kern_ms * 1e-3) / 1e9,
-                             "peak": smem_peak, "unit": "GB/s",
-                             "frac": gather_bytes / (kern_ms * 1e-3) / 1e9 / smem_peak,
-                             "bytes_per_launch": gather_bytes}
+    roofline["secondary"] = {"bound": "shared-memory gathers of the arc-per-record formulation (6 fp32 operands per arc and frame)",
+                             "achieved": gather_bytes / (kern_ms * 1e-3) / 1e9, "peak": smem_peak, "unit": "GB/s",
+                             "frac": gather_bytes / (kern_ms * 1e-3) / 1e9 / smem_peak, "bytes_per_launch": gather_bytes}
 
-    cpu_baseline = None
+    # -------- parity on the bench tensors + the reference's CPU path timed on this box (same estimator as --impl reference)
+    cpu_baseline, parity = None, {}
     if not a.no_cpu_baseline and world == 1:
         try:
-            per_seq_s = 2.0 * K * T / (3.0e7 if mode == "logden" else 3.4e8)
-            cores = min(os.cpu_count() or 1, 64)
-            sample = a.cpu_sample or max(cores, min(B, int(cores * 4.0 / per_seq_s) or 1))
-            sample = min(sample, B)
-            walls, workers, kind, _ = cpu_reference_run(a.config, a.variant, sample, 2)
-            w = min(walls)
-            cpu_baseline = {"value": sample * T / w, "unit": UNIT, "cores": workers, "kind": kind,
-                            "sample": "%d of %d utterances x T=%d, best of 2 passes, %d host processes" % (sample, B, T, workers)}
+            sample = cpu_sample_size(spec, 2.0, a.cpu_sample)
+            if mode == "loss":
+                sample = B
+            grad_for = sorted(set(range(0, sample, max(1, sample // 12))) | {sample - 1})
+            ref = cpu_reference(spec, sample, 3, grad_for=grad_for)
+            cpu_baseline = {"value": ref["value"], "unit": UNIT, "cores": ref["workers"], "kind": ref["kind"],
+                            "sample": ref["desc"]}
+            if mode == "loss":
+                mine, want = objf, -(ref["objf_num"] - ref["objf"])
+                gerr = max(float((r.grad[b].cpu() - (torch.from_numpy(ref["grads"][b][0]) - torch.from_numpy(ref["grads"][b][1]))).abs().max())
+                           for b in grad_for)
+            else:
+                mine, want = float(r.logp[:sample].double().sum()), ref["objf"]
+                gerr = max(float((r.grad[b].cpu() - torch.from_numpy(ref["grads"][b])).abs().max()) for b in grad_for)
+            parity = {"objf_rel_err": abs(mine - want) / max(1e-30, abs(want)), "grad_max_abs_err": gerr,
+                      "parity_vs": "%s CPU path, same tensors, objf over utterances [0,%d), grad over %d of them" % (
+                          ref["kind"], sample, len(grad_for)),
+                      "objf_ref": want, "objf_mine": mine}
         except Exception as ex:  # the baseline must never take the bench line down
-            cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)[:200]}
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)[:300]}
+
+    # -------- the reference's own CUDA path on this GPU, same tensors
+    ref_cuda = None
+    if not a.no_ref_cuda and world == 1 and mode in ("den", "logden"):
+        try:
+            ref_cuda = reference_cuda_leg(spec, graph, x_dev, lengths, r, dev)
+        except Exception as ex:
+            ref_cuda = {"value": None, "error": repr(ex)[:300]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": workload_name(a.config, a.variant, c), "global_batch": B * world, "frames_per_step": frames * world,
-                   "parallelism": "batch-shard x%d, one NCCL sum of {objf,frames,ok}" % world,
-                   "l2": "inputs (%.0f MB x + %.0f MB alpha spill per step) exceed the 126 MB L2; no flush needed" % (
-                       B * T * D * 4 / 1e6, B * (T + 1) * S * 4 / 1e6)},
-        "objf": objf, "ok": ok,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config_dict(a, spec, world),
+        "objf": objf_global, "ok": ok,
+        "objf_rel_err": parity.get("objf_rel_err"), "grad_max_abs_err": parity.get("grad_max_abs_err"), "parity": parity,
         "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": B * T * D * 4,
-                "d2h_bytes_per_step": 4, "api": "pychain_b200.%s; pinned host x -> device every step (copy of step i+1 overlaps step i), objf.item() every step" % ("ChainLoss.forward + backward" if mode == "loss" else "ChainFunction.apply")},
+                "d2h_bytes_per_step": 4,
+                "h2d_ms_alone": h2d_ms, "pcie_ceiling": frames_global / (h2d_ms * 1e-3),
+                "api": "pychain_b200.%s; pinned host x -> device every step (copy of step i+1 overlaps step i); the step's "
+                       "result read back is the 4-byte objective (objf.item()) -- the gradient stays on the device for the "
+                       "network's backward, as in training; pcie_ceiling = frames / (H2D of one step's x alone)" % (
+                           "ChainLoss.forward + backward" if mode == "loss" else "ChainFunction.apply")},
         "gpu_launches": launches,
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_cuda": ref_cuda, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def reference_cuda_leg(spec, graph, x_dev, lengths, mine, dev):
+    """The UNMODIFIED reference extension's CUDA path (chain-computation.cc:118-135, 256-270 ->
+    chain-kernels.cu:247-300; compiled for sm_100 by oracle/build_ref.py) on the bench tensors: the number
+    north_star asks to sit next to.  The reference re-uploads the (B-fold replicated) graph on every call
+    (chain-computation.cc:77-89); that upload is timed separately as well."""
+    import torch
+    from oracle import chain_oracle as co
+    from pychain_b200 import ChainGraphBatch
+    if not co.ref_available():
+        return {"value": None, "error": "oracle/_ref not built"}
+    B, T = spec["B"], spec["T"]
+    mode = spec["mode"]
+    gbm = ChainGraphBatch(graph, B).materialize()      # what graph.py:101-120 builds on the host every step
+    xc = x_dev.clamp(-30, 30)
+    xin = xc.exp() if mode == "den" else xc
+    call = (lambda: co.den_ref(gbm, xin, lengths, spec["coeff"])) if mode == "den" else (lambda: co.num_ref(gbm, xin, lengths))
+    times = []
+    out = None
+    for i in range(4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = call()
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    names = ["forward_transitions", "forward_transition_indices", "forward_transition_probs", "backward_transitions",
+             "backward_transition_indices", "backward_transition_probs", "initial_probs", "final_probs"] + (
+                 ["leaky_probs"] if mode == "den" else [])
+    ups = []
+    for i in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        keep = [getattr(gbm, n).to(dev) for n in names]
+        torch.cuda.synchronize()
+        ups.append(time.perf_counter() - t0)
+        del keep
+    sec, up = median(times[1:]), median(ups)
+    frames = int(lengths.sum())
+    g_ref = out[1].exp() if mode == "logden" else out[1]
+    res = {"value": frames / sec, "unit": UNIT, "ms_per_call": sec * 1e3, "graph_upload_ms": up * 1e3,
+           "value_without_graph_upload": frames / max(1e-9, sec - up), "B": B,
+           "what": "oracle/_ref (unmodified reference, sm_100) CUDA path, wall clock around the call incl. its host loop, "
+                   "its per-call H2D of the replicated graph and its syncs; median of 3 warm calls",
+           "objf_rel_err_vs_ours": abs(float(out[0]) - float(mine.objf)) / max(1e-30, abs(float(out[0]))),
+           "grad_max_abs_err_vs_ours": float((g_ref - mine.grad).abs().max())}
+    return res
 
 
 if __name__ == "__main__":

@@ -87,7 +87,10 @@ size_t chain_b200_workspace_bytes(int B, int T, int D, int S, int K, unsigned fl
  * grad_dev   f32 [B,T,D]  d objf / d log-prob = arc posteriors summed per pdf; rows t >= len are 0.
  *                         Every element is written (no pre-zeroing needed).
  * ok_dev     i32 [1]      the reference's self-check verdict (chain-computation.cc:345-391), 1 = ok
- * diag_dev   f32 [2]      {sum_b sum_i alpha'(0,i) beta'(0,i), sum_b sum_n gamma(0,n)} (may be NULL) */
+ * diag_dev   f32 [8]      {sum_b sum_i alpha'(0,i) beta'(0,i), sum_b sum_n gamma(0,n), objf, valid frames
+ *                         (sum_b min(len_b, T)), 1 - ok, 0, 0, 0} (may be NULL).  Elements 2..4 are the numbers a
+ *                         batch-sharded job sums over ranks (chain-computation.cc:229, loss.py:104): one
+ *                         contiguous buffer for ONE all-reduce, no further launch. */
 int chain_b200_forward_backward(
     const int32_t *fwd_trans_dev, const int32_t *fwd_idx_dev, const float *fwd_probs_dev,
     const int32_t *bwd_trans_dev, const int32_t *bwd_idx_dev, const float *bwd_probs_dev,
@@ -99,7 +102,7 @@ int chain_b200_forward_backward(
 
 /* Numerator-style forward-backward: log domain, no leaky HMM.
  * grad_dev holds log-posteriors when CHAIN_B200_GRAD_AS_LOG is set (rows t >= len are -inf),
- * posteriors otherwise (rows t >= len are 0).  diag_dev f32 [1] = sum_b sum_n gamma(0,n). */
+ * posteriors otherwise (rows t >= len are 0).  diag_dev f32 [8] as above with element 0 unused (= 0). */
 int chain_b200_forward_backward_log_domain(
     const int32_t *fwd_trans_dev, const int32_t *fwd_idx_dev, const float *fwd_probs_dev,
     const int32_t *bwd_trans_dev, const int32_t *bwd_idx_dev, const float *bwd_probs_dev,

@@ -18,8 +18,8 @@ extern thread_local int g_launch_count;
 extern int g_verbose_level;
 
 // objf = sum_b logp[b]; ok = the reference's t=0 self-check (defined in generic.cu)
-void launch_finalize(const float *logp, const float *diag, int B, int check_ab, float *objf, int32_t *ok,
-                     float *diag_out, cudaStream_t stream);
+void launch_finalize(const float *logp, const float *diag, const int64_t *lengths, int B, int T, int check_ab,
+                     float *objf, int32_t *ok, float *diag_out, cudaStream_t stream);
 
 struct DeviceGuard {
   int prev = -1;

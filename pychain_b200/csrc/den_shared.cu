@@ -564,7 +564,7 @@ int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev,
     const int st = launch_den_shared_log(h, p, G, l1c, grid, smem, stream);
     if (st != 0) return st;
     g_launch_count++;
-    launch_finalize(p.logp, p.diag, B, 0, objf, ok, diag, stream);
+    launch_finalize(p.logp, p.diag, lengths, B, T, 0, objf, ok, diag, stream);
     g_launch_count++;
     return (int)cudaGetLastError();
   }
@@ -585,7 +585,7 @@ int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev,
   }
 #undef LAUNCH_DEN
   g_launch_count++;
-  launch_finalize(p.logp, p.diag, B, 1, objf, ok, diag, stream);
+  launch_finalize(p.logp, p.diag, lengths, B, T, 1, objf, ok, diag, stream);
   g_launch_count++;
   e = cudaGetLastError();
   return (int)e;

@@ -401,21 +401,29 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
 // ---------------------------------------------------------------- finalize
 // objf = sum_b logp[b] (fixed order, double); ok = the reference's t=0 self-check
 // (chain-computation.cc:345-391 / chain-log-domain-computation.cc:283-304).
+// diag_out (8 floats): {alpha.beta sum, gamma sum, objf, valid frames, not ok, 0, 0, 0}; elements 2..4 are the
+// three numbers the batch-sharded loss all-reduces (the reference's only cross-utterance operations:
+// chain-computation.cc:229 and loss.py:104), ready in one contiguous buffer with no further launch.
 __global__ void __launch_bounds__(256) finalize_kernel(const float *__restrict__ logp, const float *__restrict__ diag,
-                                                       int B, int check_ab, float *objf, int32_t *ok,
-                                                       float *diag_out) {
-  __shared__ double sh[3][256];
+                                                       const int64_t *__restrict__ lengths, int B, int T,
+                                                       int check_ab, float *objf, int32_t *ok, float *diag_out) {
+  __shared__ double sh[4][256];
   const int tid = threadIdx.x;
-  double a = 0.0, ab = 0.0, gs = 0.0;
+  double a = 0.0, ab = 0.0, gs = 0.0, fr = 0.0;
   for (int b = tid; b < B; b += 256) {
     a += (double)logp[b];
     ab += (double)diag[2 * b];
     gs += (double)diag[2 * b + 1];
+    const long long l = lengths ? lengths[b] : 0;
+    fr += (double)(l < 0 ? 0 : (l > T ? T : l));
   }
-  sh[0][tid] = a; sh[1][tid] = ab; sh[2][tid] = gs;
+  sh[0][tid] = a; sh[1][tid] = ab; sh[2][tid] = gs; sh[3][tid] = fr;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
-    if (tid < o) { sh[0][tid] += sh[0][tid + o]; sh[1][tid] += sh[1][tid + o]; sh[2][tid] += sh[2][tid + o]; }
+    if (tid < o) {
+      sh[0][tid] += sh[0][tid + o]; sh[1][tid] += sh[1][tid + o]; sh[2][tid] += sh[2][tid + o];
+      sh[3][tid] += sh[3][tid + o];
+    }
     __syncthreads();
   }
   if (tid == 0) {
@@ -427,13 +435,16 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float *__restrict__
     if (!(fabsf(gsm - bsz) < gsm * 0.01f) && (fabsf(gsm - bsz) > 0.05f * bsz || gsm - gsm != 0.f)) good = 0;
     if (!(abp - abp == 0.f) || !(obj - obj == 0.f)) good = 0;  // NaN / inf anywhere
     *ok = good;
-    if (diag_out) { diag_out[0] = abp; diag_out[1] = gsm; }
+    if (diag_out) {
+      diag_out[0] = abp; diag_out[1] = gsm; diag_out[2] = obj; diag_out[3] = (float)sh[3][0];
+      diag_out[4] = good ? 0.f : 1.f; diag_out[5] = diag_out[6] = diag_out[7] = 0.f;
+    }
   }
 }
 
-void launch_finalize(const float *logp, const float *diag, int B, int check_ab, float *objf, int32_t *ok,
-                     float *diag_out, cudaStream_t stream) {
-  finalize_kernel<<<1, 256, 0, stream>>>(logp, diag, B, check_ab, objf, ok, diag_out);
+void launch_finalize(const float *logp, const float *diag, const int64_t *lengths, int B, int T, int check_ab,
+                     float *objf, int32_t *ok, float *diag_out, cudaStream_t stream) {
+  finalize_kernel<<<1, 256, 0, stream>>>(logp, diag, lengths, B, T, check_ab, objf, ok, diag_out);
 }
 
 // ---------------------------------------------------------------- host side
@@ -529,7 +540,7 @@ static int run_generic(const int32_t *ft, const int32_t *fi, const float *fp, co
   }
   kern<<<B, nt, smem, stream>>>(p);
   g_launch_count++;
-  launch_finalize(p.logp, p.diag, B, LOG ? 0 : 1, objf, ok, diag, stream);
+  launch_finalize(p.logp, p.diag, p.lengths, B, T, LOG ? 0 : 1, objf, ok, diag, stream);
   g_launch_count++;
   e = cudaGetLastError();
   return (int)e;

@@ -14,7 +14,7 @@ sorted descending (what `ChainFunction` requires).
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_indices", "shard_batch", "reduce_stats", "sharded_objf"]
+__all__ = ["shard_indices", "shard_batch", "reduce_stats", "reduce_result", "sharded_objf"]
 
 
 def shard_indices(batch_size, rank, world_size):
@@ -41,6 +41,16 @@ def reduce_stats(objf, frames, ok, group=None):
     buf = torch.stack([objf.reshape(()).float(),
                        torch.as_tensor(float(frames), device=objf.device),
                        (1 - ok.reshape(-1)[0].float()) if torch.is_tensor(ok) else torch.as_tensor(0.0 if ok else 1.0, device=objf.device)])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return buf[0], buf[1], buf[2] == 0
+
+
+def reduce_result(r, group=None):
+    """The same single collective for an engine `Result`: its `stats` view already holds
+    {objf, valid frames, not ok} (written by the finalize kernel), so the step costs ONE all-reduce and no
+    other launch or host-to-device write.  Returns (objf_sum, frames_sum, all_ok) tensors."""
+    buf = r.stats
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     return buf[0], buf[1], buf[2] == 0

@@ -32,10 +32,13 @@ def launch_count():
 
 class Result(object):
     """Outputs of one forward-backward: all device tensors, nothing synchronised."""
-    __slots__ = ("objf", "logp", "grad", "ok", "diag")
+    __slots__ = ("objf", "logp", "grad", "ok", "diag", "stats")
 
     def __init__(self, objf, logp, grad, ok, diag):
-        self.objf, self.logp, self.grad, self.ok, self.diag = objf, logp, grad, ok, diag
+        # diag: the 8 floats finalize_kernel writes; [0:2] = the reference's self-check sums,
+        # [2:5] = {objf, valid frames, not ok}: the one buffer a batch-sharded job all-reduces
+        self.objf, self.logp, self.grad, self.ok = objf, logp, grad, ok
+        self.diag, self.stats = diag[:2], diag[2:5]
 
 
 def _ptr(t):
@@ -54,8 +57,17 @@ def _require_cuda(x, what):
 
 
 def _is_shared(tensors, B):
-    """True when every graph tensor is a stride-0 batch view (or B == 1)."""
+    """True when every graph tensor is a stride-0 batch view, i.e. ONE graph for the whole batch
+    (`ChainGraphBatch(graph, B)`).  A batch of one is shared in the trivial sense."""
     return B == 1 or all(t.stride(0) == 0 for t in tensors)
+
+
+def _record_side_stream(tstream, tensors):
+    """Buffers allocated from the CURRENT stream's pool but used by kernels on `tstream`: tell the caching
+    allocator, or it may hand a freed block to the current stream while the side-stream kernel still runs."""
+    for t in tensors:
+        if t is not None and t.is_cuda:
+            t.record_stream(tstream)
 
 
 def _graph_to_device(tensors, device, shared, names):
@@ -132,7 +144,7 @@ def _run_generic(log_domain, graph_tensors, x, lengths, num_states, leaky_coeffi
     logp = torch.empty(B, dtype=torch.float32, device=dev) if want_logp else None
     grad = torch.empty_like(x)
     ok = torch.empty(1, dtype=torch.int32, device=dev)
-    diag = torch.empty(2, dtype=torch.float32, device=dev)
+    diag = torch.empty(8, dtype=torch.float32, device=dev)
     ws_bytes = lib.chain_b200_workspace_bytes(B, T, D, S, K, flags)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     tstream, cstream = _launch_stream(dev, stream)
@@ -147,9 +159,8 @@ def _run_generic(log_domain, graph_tensors, x, lengths, num_states, leaky_coeffi
             _ptr(objf), _ptr(logp), _ptr(grad), _ptr(ok), _ptr(diag), _ptr(ws), ws_bytes, dev.index or 0, cstream)
         _cabi.check(st, "chain_b200_forward_backward")
     _launches += lib.chain_b200_last_launch_count()
-    if stream is not None:  # buffers of the current stream's pool used by kernels on `stream`
-        for t in (ws, x, ldev):
-            t.record_stream(tstream)
+    if stream is not None:  # every buffer of the current stream's pool that the side-stream kernels touch
+        _record_side_stream(tstream, [ws, x, ldev, objf, logp, grad, ok, diag] + list(g))
     return Result(objf, logp, grad, ok, diag)
 
 
@@ -165,9 +176,10 @@ class PreparedDenGraph(object):
 _prepared_cache = OrderedDict()
 
 
-def prepare_den_graph(graph_tensors, num_states, D, device, log_domain=False, batch_size=None):
+def prepare_den_graph(graph_tensors, num_states, D, device, log_domain=False, batch_size=None, content_key=None):
     """Pack (once; cached) a single graph given its reference-layout tensors (row 0 of each is
-    used).  `graph_tensors` order = _GRAPH_NAMES_PROB, or _GRAPH_NAMES_LOG for a log-domain graph."""
+    used).  `graph_tensors` order = _GRAPH_NAMES_PROB, or _GRAPH_NAMES_LOG for a log-domain graph.
+    The cache is keyed by the tensors' storage (pointer + version), or by `content_key` when given."""
     lib = _cabi.lib()
     names = _GRAPH_NAMES_LOG if log_domain else _GRAPH_NAMES_PROB
     rows = [t[0] if t.dim() == (3 if "transition" in n and "probs" not in n else 2) else t
@@ -176,7 +188,8 @@ def prepare_den_graph(graph_tensors, num_states, D, device, log_domain=False, ba
     dev_index = torch.device(device).index or 0
     G = lib.chain_b200_den_group_width(int(num_states), int(D), int(batch_size), dev_index) if batch_size else 4
     G = G if G in (1, 2, 4) else 4
-    key = (tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in rows), int(D), str(device), bool(log_domain), G)
+    ident = content_key if content_key is not None else tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in rows)
+    key = (ident, int(D), str(device), bool(log_domain), G)
     hit = _prepared_cache.get(key)
     if hit is not None:
         _prepared_cache.move_to_end(key)
@@ -200,7 +213,7 @@ def prepare_den_graph(graph_tensors, num_states, D, device, log_domain=False, ba
     copies = int(os.environ.get("CHAIN_B200_BLOB_COPIES", "1"))
     blob_dev = blob.to(device).repeat(copies) if torch.device(device).type == "cuda" else None
     prep = PreparedDenGraph(blob, blob_dev, copies, S, K, int(D))
-    _prepared_cache[key] = (rows, prep)
+    _prepared_cache[key] = (rows if content_key is None else None, prep)  # pointer keys: keep the sources alive
     while len(_prepared_cache) > 8:
         _prepared_cache.popitem(last=False)
     return prep
@@ -219,7 +232,7 @@ def _run_den_shared(prep, x, lengths, leaky_coefficient, flags, stream=None):
     logp = torch.empty(B, dtype=torch.float32, device=dev)
     grad = torch.empty_like(x)
     ok = torch.empty(1, dtype=torch.int32, device=dev)
-    diag = torch.empty(2, dtype=torch.float32, device=dev)
+    diag = torch.empty(8, dtype=torch.float32, device=dev)
     ws_bytes = lib.chain_b200_den_workspace_bytes(_ptr(prep.blob_host), B, T)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     tstream, cstream = _launch_stream(dev, stream)
@@ -229,8 +242,7 @@ def _run_den_shared(prep, x, lengths, leaky_coefficient, flags, stream=None):
     _cabi.check(st, "chain_b200_den_forward_backward")
     _launches += lib.chain_b200_last_launch_count()
     if stream is not None:
-        for t in (ws, x, ldev):
-            t.record_stream(tstream)
+        _record_side_stream(tstream, [ws, x, ldev, objf, logp, grad, ok, diag, prep.blob_dev])
     return Result(objf, logp, grad, ok, diag)
 
 
@@ -244,6 +256,52 @@ def _shared_fits(S, D):
 # ------------------------------------------------------------------ public helpers
 DEN_PATH = "auto"  # "auto": shared graphs use the packed shared-graph kernels; "generic": always the per-sequence kernel
 
+_FALLBACK_STATUS = ("status -1)", "status -3)")  # ERR_INVALID_ARG / ERR_UNSUPPORTED from prepare or the packed launch
+
+
+def _same_graph_everywhere(tensors, B):
+    """A MATERIALISED batch (`[B,...]` contiguous, what the reference's `ChainGraphBatch.initialized_by_one`
+    builds with `.repeat`, graph.py:101-120) whose rows all hold the same graph?  Checked on rows
+    0, B//2 and B-1 of every tensor (all rows with CHAIN_B200_STRICT_SHARED_CHECK=1): such a batch is
+    routed to the packed shared-graph kernels instead of the 8x slower per-sequence kernel."""
+    if B < 2 or any(t is None or t.dim() < 2 or t.size(0) != B for t in tensors):
+        return False
+    if os.environ.get("CHAIN_B200_STRICT_SHARED_CHECK"):
+        return all(bool((t == t[0:1]).all()) for t in tensors)
+    return all(torch.equal(t[0], t[B // 2]) and torch.equal(t[0], t[B - 1]) for t in tensors)
+
+
+def _content_key(rows):
+    """Fingerprint of a graph's tensors (row 0 of a batch): materialised batches are new tensors every step
+    (the reference re-creates them per forward, loss.py:99), so the packed-graph cache cannot key on pointers."""
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    for t in rows:
+        h.update(t.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def _shared_rows(graph_tensors, B):
+    """Row-0 tensors when the batch is ONE graph (stride-0 views, a batch of one, or a materialised batch of
+    identical rows), else None.  The second value is a content key for materialised batches."""
+    if _is_shared(graph_tensors, B):
+        return graph_tensors, None
+    if _same_graph_everywhere(graph_tensors, B):
+        rows = tuple(t[0:1] for t in graph_tensors)
+        return rows, _content_key(rows)
+    return None, None
+
+
+def _try_packed(run, fallback):
+    """Run the packed shared-graph path; graphs it cannot take (padded states in a batch of one,
+    on-chip working set too large once rows are split) go to the general kernel."""
+    try:
+        return run()
+    except ChainB200Error as e:
+        if str(e).endswith(_FALLBACK_STATUS):
+            return fallback()
+        raise
+
 
 def forward_backward_prob(graph_tensors, x, lengths, num_states, leaky_coefficient=1e-5, x_is_exp=True, clamp=False,
                           path=None, stream=None):
@@ -252,10 +310,15 @@ def forward_backward_prob(graph_tensors, x, lengths, num_states, leaky_coefficie
     flags = (X_IS_EXP if x_is_exp else 0) | (CLAMP_X if clamp else 0)
     path = path or DEN_PATH
     B = x.size(0)
-    if path != "generic" and _is_shared(graph_tensors, B) and _shared_fits(int(num_states), int(x.size(2))):
-        prep = prepare_den_graph(graph_tensors, num_states, x.size(2), x.device, batch_size=B)
-        return _run_den_shared(prep, x, lengths, leaky_coefficient, flags, stream=stream)
-    return _run_generic(False, graph_tensors, x, lengths, num_states, leaky_coefficient, flags, stream=stream)
+    generic = lambda: _run_generic(False, graph_tensors, x, lengths, num_states, leaky_coefficient, flags, stream=stream)  # noqa: E731
+    if path != "generic" and _shared_fits(int(num_states), int(x.size(2))):
+        rows, ckey = _shared_rows(graph_tensors, B)
+        if rows is not None:
+            def packed():
+                prep = prepare_den_graph(rows, num_states, x.size(2), x.device, batch_size=B, content_key=ckey)
+                return _run_den_shared(prep, x, lengths, leaky_coefficient, flags, stream=stream)
+            return _try_packed(packed, generic)
+    return generic()
 
 
 def forward_backward_log(graph_tensors, x, lengths, num_states, grad_as_log=True, clamp=False, path=None, stream=None):
@@ -265,8 +328,15 @@ def forward_backward_log(graph_tensors, x, lengths, num_states, grad_as_log=True
     flags = (GRAD_AS_LOG if grad_as_log else 0) | (CLAMP_X if clamp else 0)
     path = path or DEN_PATH
     S, K = int(num_states), int(graph_tensors[0].size(1))
-    if (path != "generic" and x.size(0) > 1 and _is_shared(graph_tensors, x.size(0)) and K >= 256
-            and S <= 32767 and x.size(2) <= 32767 and _shared_fits(S, int(x.size(2)))):
-        prep = prepare_den_graph(graph_tensors, num_states, x.size(2), x.device, log_domain=True, batch_size=x.size(0))
-        return _run_den_shared(prep, x, lengths, 0.5, flags, stream=stream)
-    return _run_generic(True, graph_tensors, x, lengths, num_states, 0.0, flags, stream=stream)
+    B = x.size(0)
+    generic = lambda: _run_generic(True, graph_tensors, x, lengths, num_states, 0.0, flags, stream=stream)  # noqa: E731
+    if (path != "generic" and B > 1 and K >= 256 and S <= 32767 and x.size(2) <= 32767
+            and _shared_fits(S, int(x.size(2)))):
+        rows, ckey = _shared_rows(graph_tensors, B)
+        if rows is not None:
+            def packed():
+                prep = prepare_den_graph(rows, num_states, x.size(2), x.device, log_domain=True, batch_size=B,
+                                         content_key=ckey)
+                return _run_den_shared(prep, x, lengths, 0.5, flags, stream=stream)
+            return _try_packed(packed, generic)
+    return generic()

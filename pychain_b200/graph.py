@@ -80,10 +80,13 @@ class Fst(object):
         return int(self.src.shape[0])
 
     @classmethod
-    def from_text(cls, lines: Iterable[str]) -> "Fst":
+    def from_text(cls, lines: Iterable[str], acceptor: bool = False) -> "Fst":
         """Parse OpenFst text format (`fstprint`): `src dst ilabel olabel [w]`
-        arc lines and `state [w]` final lines; start = source of the first line.
-        Weights are tropical/log costs, so log-prob = -w.  pdf = ilabel - 1."""
+        arc lines (`src dst label [w]` with `acceptor=True`, what `fstprint --acceptor` writes) and
+        `state [w]` final lines; start = source of the first line.
+        Weights are tropical/log costs, so log-prob = -w.  pdf = ilabel - 1.
+        A line whose field count or label fields do not fit the chosen format raises instead of being
+        misread (a 4-column acceptor line would otherwise parse as a transducer arc of weight 0)."""
         src, dst, pdf, lw = [], [], [], []
         finals = {}
         start = None
@@ -94,11 +97,22 @@ class Fst(object):
                 continue
             if start is None:
                 start = int(f[0])
-            if len(f) >= 4:
-                s, d, il = int(f[0]), int(f[1]), int(f[2])
-                w = float(f[4]) if len(f) >= 5 else 0.0
+            n_lab = 1 if acceptor else 2
+            if len(f) > 2 + n_lab + 1:
+                raise ValueError("Fst.from_text: too many fields in {!r}".format(line))
+            if len(f) >= 2 + n_lab:
+                try:
+                    s, d = int(f[0]), int(f[1])
+                    labels = [int(v) for v in f[2:2 + n_lab]]
+                except ValueError:
+                    raise ValueError("Fst.from_text: {!r} is not a{} arc line (pass acceptor={})".format(
+                        line, "n acceptor" if acceptor else " transducer", not acceptor))
+                il = labels[0]
+                w = float(f[2 + n_lab]) if len(f) > 2 + n_lab else 0.0
                 src.append(s), dst.append(d), pdf.append(il - 1), lw.append(-w)
                 nstates = max(nstates, s + 1, d + 1)
+            elif len(f) == 3 and not acceptor:
+                raise ValueError("Fst.from_text: 3-field line {!r}: acceptor format? pass acceptor=True".format(line))
             else:
                 s = int(f[0])
                 w = float(f[1]) if len(f) >= 2 else 0.0
@@ -275,10 +289,23 @@ class ChainGraphBatch(object):
         self.shared_graph = graph
         self.log_domain = graph.log_domain
         self.num_states, self.num_transitions = graph.num_states, graph.num_transitions
+        device = getattr(self, "_device", None)
         for name, _, _, pad_log in self._FIELDS:
             t = getattr(graph, name)
+            if t is not None and device is not None:
+                t = self._on_device(graph, name, t, device)
             setattr(self, name, None if t is None else t.unsqueeze(0).expand(B, *t.shape))
-        self.start_state = torch.full((B,), int(graph.start_state), dtype=torch.long)
+        self.start_state = torch.full((B,), int(graph.start_state), dtype=torch.long, device=device)
+
+    @staticmethod
+    def _on_device(graph, name, t, device):
+        """The single graph's tensor on `device`, moved once per (graph, device) and cached on the graph."""
+        cache = graph.__dict__.setdefault("_device_tensors", {})
+        key = (name, str(device), t.data_ptr(), t._version)
+        hit = cache.get(key)
+        if hit is None:
+            hit = cache[key] = t.to(device)
+        return hit
 
     def initialized_by_list(self, graphs, max_num_transitions, max_num_states):
         """Per-utterance graphs stacked with zero / -inf padding (`graph.py:122-175`): padded
@@ -323,6 +350,12 @@ class ChainGraphBatch(object):
     def to(self, device):
         """Move the batch tensors to `device` once, instead of the reference's per-call
         `.cuda()` inside the extension (`chain-computation.cc:77-89`)."""
+        if self.shared_graph is not None:
+            # `.to()` of a stride-0 expand view would materialise B copies (and the engine would then take the
+            # per-sequence kernel): move the ONE graph and re-expand; `reorder` stays on this device too
+            self._device = torch.device(device)
+            self.initialized_by_one(self.shared_graph)
+            return self
         for name in self._BATCH_FIELDS:
             t = getattr(self, name)
             if t is not None:

@@ -20,32 +20,73 @@ Differences from the reference, all permitted by its contract:
   * `start_state` and `batch_sizes` are accepted and ignored; the reference never
     reads `start_state` (SURVEY.md Appx C-12) and uses `batch_sizes` only to
     express "sequence b is alive at frame t", which `sequence_lengths` already says.
-  * `ok` is returned as a CPU bool[1] tensor like the reference (this synchronises;
-    `pychain_b200.loss` uses the engine directly and does not).
+  * `ok` is returned as a CPU bool[1] tensor like the reference.  The reference fills it after
+    `.item()` syncs; here it is a pinned host tensor filled by an ASYNCHRONOUS device-to-host copy on the
+    current stream, so the call itself does not synchronise (the reference's only caller ignores `ok`,
+    loss.py:44,62).  Its value is valid after any later synchronisation of that stream (`objf.item()`,
+    `torch.cuda.synchronize()`); at verbose level >= 1 the call synchronises and reports like the reference.
 """
 import torch
 
 from . import _cabi, engine
 
 
-def _report(r, batch, log_domain):
-    """What the reference's self-check prints to stderr (chain-computation.cc:363-390,
-    chain-log-domain-computation.cc:289-303), from the device-side diagnostics: on failure, and
-    always at verbose level >= 1 (the reference re-checks every frame then; here frame 0 is the
-    one that accumulates the whole backward recursion)."""
+_ok_ring = []      # pinned bool[1] buffers, reused round-robin (cudaHostAlloc per call would serialise)
+_ok_next = 0
+_ok_pending = []   # (event, buffer) of calls whose verdict has not been looked at yet
+
+
+def poll_reports(wait=False):
+    """Print the reference's failure line for every earlier call whose asynchronous self-check has completed
+    and failed.  Called at the start of every forward_backward*; call it with wait=True (after a
+    synchronisation point of your own) to flush."""
     import sys
-    ok = bool(r.ok.item())
+    keep = []
+    for ev, buf in _ok_pending:
+        if wait:
+            ev.synchronize()
+        if ev.query():
+            if not bool(buf[0]):
+                print("Excessive error detected, will abandon this minibatch", file=sys.stderr)
+        else:
+            keep.append((ev, buf))
+    _ok_pending[:] = keep
+
+
+def _ok_host(ok_dev):
+    """bool[1] CPU tensor that receives `ok` by an async copy on the current stream."""
+    global _ok_next
+    if not _ok_ring:
+        _ok_ring.extend(torch.ones(1, dtype=torch.bool).pin_memory() for _ in range(64))
+    if len(_ok_pending) >= len(_ok_ring) - 1:   # never hand out a buffer that is still pending
+        poll_reports(wait=True)
+    buf = _ok_ring[_ok_next % len(_ok_ring)]
+    _ok_next += 1
+    buf.copy_(ok_dev != 0, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(ok_dev.device))
+    _ok_pending.append((ev, buf))
+    return buf
+
+
+def _report(r, batch, log_domain):
+    """`ok` for the caller + what the reference's self-check prints to stderr
+    (chain-computation.cc:363-390, chain-log-domain-computation.cc:289-303) from the device-side
+    diagnostics.  Quiet level: no synchronisation.  Verbose level >= 1: synchronise, report always
+    (the reference re-checks every frame then; here frame 0 accumulates the whole backward recursion)."""
+    import sys
     verbose = _cabi.lib().chain_b200_get_verbose_level() >= 1
-    if ok and not verbose:
-        return ok
+    poll_reports()
+    if not verbose:
+        return _ok_host(r.ok)
+    ok = bool(r.ok.item())
     ab, gs = (float(v) for v in r.diag.tolist())
-    if not log_domain and (verbose or abs(ab - batch) >= ab * 0.01):
+    if not log_domain:
         print("On time 0, alpha-beta product {} != {}".format(ab, batch), file=sys.stderr)
-    if verbose or abs(gs - batch) >= gs * 0.01:
-        print("On time 0, log-prob-deriv sum {} != {}".format(gs, batch), file=sys.stderr)
+    print("On time 0, log-prob-deriv sum {} != {}".format(gs, batch), file=sys.stderr)
     if not ok:
         print("Excessive error detected, will abandon this minibatch", file=sys.stderr)
-    return ok
+    return torch.full((1,), ok, dtype=torch.bool)
 
 
 def _check_contiguous(t, name):
@@ -65,8 +106,7 @@ def forward_backward(forward_transitions, forward_transition_indices, forward_tr
         _check_contiguous(t, n)
     r = engine.forward_backward_prob(g, exp_nnet_output, sequence_lengths, num_states, leaky_hmm_coefficient,
                                      x_is_exp=True, clamp=False)
-    ok = _report(r, exp_nnet_output.size(0), False)
-    return [r.objf, r.grad, torch.full((1,), ok, dtype=torch.bool)]
+    return [r.objf, r.grad, _report(r, exp_nnet_output.size(0), False)]
 
 
 def forward_backward_log_domain(forward_transitions, forward_transition_indices, forward_transition_probs,
@@ -79,8 +119,7 @@ def forward_backward_log_domain(forward_transitions, forward_transition_indices,
     for t, n in zip(g, engine._GRAPH_NAMES_LOG):
         _check_contiguous(t, n)
     r = engine.forward_backward_log(g, nnet_output, sequence_lengths, num_states, grad_as_log=True, clamp=False)
-    ok = _report(r, nnet_output.size(0), True)
-    return [r.objf, r.grad, torch.full((1,), ok, dtype=torch.bool)]
+    return [r.objf, r.grad, _report(r, nnet_output.size(0), True)]
 
 
 def set_verbose_level(level):

@@ -23,7 +23,8 @@ import torch
 
 from .graph import Fst, ChainGraph, ChainGraphBatch
 
-__all__ = ["random_den_fst", "linear_num_fst", "make_inputs", "make_num_batch", "CONFIGS", "den_graph_for"]
+__all__ = ["random_den_fst", "linear_num_fst", "make_inputs", "make_lengths", "input_block", "make_num_batch", "CONFIGS",
+           "den_graph_for", "workload_spec", "build_workload"]
 
 
 def random_den_fst(S: int, K: int, D: int, seed: int = 0, variant: str = "uniform") -> Fst:
@@ -98,9 +99,32 @@ def linear_num_fst(n_phones: int, D: int, seed: int = 0, states_per_phone: int =
     return Fst(S, 0, src, dst, pdf, np.asarray(lw, dtype=np.float32), fin)
 
 
-def make_inputs(B: int, T: int, D: int, seed: int = 0, variable: bool = False, device="cpu"):
+def input_block(T: int, D: int, seed: int, index: int, block: int) -> torch.Tensor:
+    """Block `index` (utterances index*block .. +block) of a blocked input tensor: every block has its own
+    generator, so a host process that only needs some utterances (the sharded CPU reference of
+    bench.py / the at-size parity tests) can regenerate exactly those without the whole [B,T,D] tensor."""
+    g = torch.Generator().manual_seed(seed * 1000003 + 7 * index + 1)
+    return 2.0 * torch.randn(block, T, D, generator=g, dtype=torch.float32)
+
+
+def make_lengths(B: int, T: int, seed: int = 0, variable: bool = False) -> torch.Tensor:
+    """lengths [B] int64, sorted descending, max == T (the `pack_padded_sequence` contract, loss.py:37-40)."""
+    if not variable:
+        return torch.full((B,), T, dtype=torch.long)
+    g = torch.Generator().manual_seed(seed + 77)
+    lengths = torch.randint(max(1, T // 2), T + 1, (B,), generator=g, dtype=torch.long)
+    lengths[0] = T
+    return torch.sort(lengths, descending=True)[0]
+
+
+def make_inputs(B: int, T: int, D: int, seed: int = 0, variable: bool = False, device="cpu", block: int = 0):
     """x [B,T,D] fp32 (unnormalised, like chain nnet outputs) and lengths [B]
-    int64, sorted descending, max == T."""
+    int64, sorted descending, max == T.  With `block` > 0 the tensor is generated in independent
+    blocks of `block` utterances (see `input_block`)."""
+    if block:
+        nb = (B + block - 1) // block
+        x = torch.cat([input_block(T, D, seed, i, block) for i in range(nb)], 0)[:B].contiguous()
+        return x.to(device), make_lengths(B, T, seed, variable)
     g = torch.Generator().manual_seed(seed)
     x = 2.0 * torch.randn(B, T, D, generator=g, dtype=torch.float32)
     if variable:
@@ -132,8 +156,46 @@ CONFIGS = {
     "cfg2": dict(S=1000, K=5000, B=64, T=150, D=256, variable=False, what="den ~1k states/5k arcs"),
     "cfg3": dict(S=1000, K=5000, B=128, T=150, D=512, variable=True, what="full ChainLoss num+den, variable T"),
     "cfg4": dict(S=5000, K=40000, B=512, T=200, D=1000, variable=False, what="biphone den ~5k states/40k arcs (headline)"),
-    "cfg5": dict(S=1000, K=5000, B=512, T=150, D=512, variable=False, what="per-GPU shard of the B=4096 batch"),
+    "cfg5": dict(S=1000, K=5000, B=512, T=150, D=512, variable=False, B_global=4096,
+                 what="per-GPU shard of the B=4096 batch"),
 }
+
+
+def workload_spec(cfg: str, variant: str = "uniform", rank: int = 0, **over) -> dict:
+    """The BASELINE configuration `cfg` as a seeded description every arm of bench.py and the at-size parity
+    tests regenerate their tensors from (graph seed 1000+idx, inputs 2000+idx in blocks of 8 utterances)."""
+    c = CONFIGS[cfg]
+    idx = int(cfg[3:])
+    mode = {"cfg2": "logden", "cfg3": "loss"}.get(cfg, "den")
+    spec = dict(cfg=cfg, mode=mode, S=c["S"], K=c["K"], D=c["D"], T=c["T"], B=c["B"], variant=variant,
+                graph_seed=1000 + idx, x_seed=2000 + idx + 7919 * rank, block=8, variable=c["variable"], coeff=1e-5,
+                num_seed=52 + 1000 * rank)
+    spec.update(over)
+    return spec
+
+
+def build_workload(spec: dict, start: int = 0, count: int = None):
+    """(den ChainGraph, numerator ChainGraphBatch or None, x [count,T,D], lengths [count]) for utterances
+    start..start+count of `spec`; only the blocks of x that are needed are generated."""
+    T, D, B, blk = spec["T"], spec["D"], spec["B"], spec["block"]
+    count = B - start if count is None else count
+    lengths = make_lengths(B, T, spec["x_seed"], spec.get("variable", False))[start:start + count]
+    b0, b1 = start // blk, (start + count + blk - 1) // blk
+    x = torch.cat([input_block(T, D, spec["x_seed"], i, blk) for i in range(b0, b1)], 0)
+    x = x[start - b0 * blk: start - b0 * blk + count].contiguous()
+    if spec.get("x_scale"):
+        x = x * float(spec["x_scale"])
+    fst = random_den_fst(spec["S"], spec["K"], D, seed=spec["graph_seed"], variant=spec.get("variant", "uniform"))
+    den = ChainGraph(fst, log_domain=(spec["mode"] == "logden"),
+                     initial_mode=spec.get("initial_mode", "fst"), final_mode=spec.get("final_mode", "fst"))
+    num = None
+    if spec["mode"] == "loss":
+        import copy
+        num = copy.copy(make_num_batch(B, T, D, seed=spec["num_seed"]))
+        if start != 0 or count != B:
+            num.reorder(torch.arange(start, start + count))
+            num.batch_size = count
+    return den, num, x, lengths
 
 
 def den_graph_for(cfg: str, variant: str = "uniform", initial_mode: str = "fst", final_mode: str = "fst") -> ChainGraph:

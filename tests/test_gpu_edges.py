@@ -125,6 +125,9 @@ def test_ok_flag_and_verbose_report(cuda, capfd):
                        gb.leaky_probs, gb.initial_probs, gb.final_probs, gb.start_state,
                        xx.exp().to(cuda), None, lengths, gb.num_states, 1e-5)
     objf, grad, ok = new_C.forward_backward(*args(x))
+    assert ok.device.type == "cpu" and ok.dtype == torch.bool and ok.is_pinned()   # filled asynchronously: no sync in the call
+    torch.cuda.synchronize()
+    new_C.poll_reports()
     assert bool(ok.item()) and capfd.readouterr().err == ""
     new_C.set_verbose_level(1)
     try:
@@ -136,6 +139,8 @@ def test_ok_flag_and_verbose_report(cuda, capfd):
     bad = x.clone()
     bad[1, 2, :] = float("nan")
     objf, grad, ok = new_C.forward_backward(*args(bad))
+    torch.cuda.synchronize()
+    new_C.poll_reports()      # the quiet-level check is asynchronous: the failure line is printed once its copy has landed
     err = capfd.readouterr().err
     assert not bool(ok.item()) and "Excessive error detected" in err
     for path in ("generic", "auto"):  # both kernels flag it on the device

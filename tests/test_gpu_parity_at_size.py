@@ -1,0 +1,100 @@
+"""Parity AT BASELINE SIZES against the reference itself (Next #1).
+
+The CUDA kernels run the BASELINE configurations at full size; the UNMODIFIED reference extension
+(`oracle/_ref`, its exact CPU path, chain-computation.cc / chain-log-domain-computation.cc) runs the
+SAME tensors sharded over the box's host cores (oracle/ref_parallel.py -- the way bench.py's CPU leg
+does), and objf (BASELINE.json: "objf within 1e-4 relative of the reference"; asserted at 5e-6) and
+the gradient of utterances spread over every group position (<= 2e-5 abs) are compared.
+When the prebuilt reference extension is absent the fp32 C restatement (oracle/chain_oracle.c, pinned
+to the reference by tests/golden) stands in.
+"""
+import os
+
+import pytest
+import torch
+
+from pychain_b200 import ChainGraph, ChainGraphBatch, ChainLoss, synth, engine
+from oracle import ref_parallel as rp
+
+pytestmark = pytest.mark.gpu
+
+OBJF_RTOL = 5e-6
+GRAD_ATOL = 2e-5
+
+
+def rel(a, b):
+    return abs(float(a) - float(b)) / max(1e-30, abs(float(b)))
+
+
+def _gpu_inputs(spec, cuda):
+    den, num, x, lengths = rp.build_inputs(spec, 0, spec["B"])
+    return den, num, x.to(cuda), lengths
+
+
+@pytest.mark.parametrize("variant", ["uniform", "biphone", "skew"])
+def test_cfg4_den_vs_reference_at_size(cuda, variant):
+    """cfg4 (S=5000, K=40000, B=512, T=200, D=1000): all 512 utterances, every variant of the graph."""
+    spec = rp.spec_for("cfg4", variant)
+    B = spec["B"]
+    grad_for = [0, 1, 2, 3, 129, 258, 387, 511] + list(range(8, B, 37))   # every position inside a group of 4
+    ref = rp.run(spec, grad_for=grad_for)
+    den, _, xd, lengths = _gpu_inputs(spec, cuda)
+    gb = ChainGraphBatch(den, B)
+    gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_PROB)
+    r = engine.forward_backward_prob(gt, xd, lengths, spec["S"], spec["coeff"], x_is_exp=False, clamp=True)
+    assert ref["ok"] and int(r.ok.item()) == 1
+    assert rel(r.objf.item(), ref["objf"]) < OBJF_RTOL, (r.objf.item(), ref["objf"])
+    worst = max((r.grad[b].cpu() - torch.from_numpy(ref["grads"][b])).abs().max().item() for b in grad_for)
+    assert worst < GRAD_ATOL, worst
+
+
+def test_cfg2_log_domain_vs_reference_at_size(cuda):
+    """cfg2: leaky-free denominator (S=1000, K=5000, B=64, T=150, D=256) through the LOG-domain entry."""
+    spec = rp.spec_for("cfg2")
+    B = spec["B"]
+    grad_for = list(range(0, B, 5))
+    ref = rp.run(spec, grad_for=grad_for)
+    den, _, xd, lengths = _gpu_inputs(spec, cuda)
+    gb = ChainGraphBatch(den, B)
+    gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_LOG)
+    r = engine.forward_backward_log(gt, xd, lengths, spec["S"], grad_as_log=False, clamp=True)
+    assert ref["ok"] and int(r.ok.item()) == 1
+    assert rel(r.objf.item(), ref["objf"]) < OBJF_RTOL
+    worst = max((r.grad[b].cpu() - torch.from_numpy(ref["grads"][b])).abs().max().item() for b in grad_for)
+    assert worst < GRAD_ATOL, worst
+
+
+def test_cfg3_chain_loss_vs_reference_at_size(cuda):
+    """cfg3: full ChainLoss (per-utterance numerators + shared denominator, leaky 1e-5), B=128, D=512,
+    variable T: loss = -(num - den), d loss/dx = gamma_den - gamma_num (loss.py:97-105, avg=False)."""
+    spec = rp.spec_for("cfg3")
+    B = spec["B"]
+    grad_for = list(range(0, B, 9)) + [B - 1]
+    ref = rp.run(spec, grad_for=grad_for)
+    den, num, xd, lengths = _gpu_inputs(spec, cuda)
+    xg = xd.requires_grad_(True)
+    loss = ChainLoss(den, leaky_coefficient=spec["coeff"], avg=False)(xg, lengths, num)
+    loss.backward()
+    want = -(ref["objf_num"] - ref["objf"])
+    assert ref["ok"]
+    assert rel(loss.item(), want) < 2e-5, (loss.item(), want)   # a difference of two objfs of opposite sign
+    worst = 0.0
+    for b in grad_for:
+        g = torch.from_numpy(ref["grads"][b])
+        worst = max(worst, (xg.grad[b].cpu() - (g[0] - g[1])).abs().max().item())
+    assert worst < 2 * GRAD_ATOL, worst
+
+
+def test_cfg5_shard_vs_reference_at_size(cuda):
+    """The 512-utterance per-GPU shard of cfg5 (B=4096 over 8 GPUs, T=150, D=512, S=1000/K=5000)."""
+    spec = rp.spec_for("cfg5")
+    B = spec["B"]
+    grad_for = list(range(0, B, 41))
+    ref = rp.run(spec, grad_for=grad_for)
+    den, _, xd, lengths = _gpu_inputs(spec, cuda)
+    gb = ChainGraphBatch(den, B)
+    gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_PROB)
+    r = engine.forward_backward_prob(gt, xd, lengths, spec["S"], spec["coeff"], x_is_exp=False, clamp=True)
+    assert rel(r.objf.item(), ref["objf"]) < OBJF_RTOL
+    worst = max((r.grad[b].cpu() - torch.from_numpy(ref["grads"][b])).abs().max().item() for b in grad_for)
+    assert worst < GRAD_ATOL, worst
