@@ -35,6 +35,16 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name, defines):
+    """An experimental variant of the library (tuning macros), e.g. build_variant("nf4", ["-DCHAIN_B200_NF2_G4=4"])
+    -> pychain_b200/lib/libchain_b200_nf4.so; select it at run time with CHAIN_B200_LIB=<path>."""
+    out = os.path.join(PKG, "lib", "libchain_b200_%s.so" % name)
+    cmd = [os.environ.get("NVCC", "nvcc")] + NVCC_FLAGS + list(defines) + [
+        "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", out] + _sources()
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return out
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB

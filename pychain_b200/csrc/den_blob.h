@@ -22,13 +22,28 @@
 // over (max, sum-exp) pairs instead of plain partial sums.
 // Rows whose degree exceeds the view's cap are split into sub-rows; a sub-row writes its
 // partial sum to a scratch slot and the listed owner adds the slots up in order.
+//
+// (dst, pdf) CLASSES (probability-domain blobs).  In chain denominator graphs the pdf of an arc is (almost) a
+// function of its destination (pdf = ilabel - 1 sits on the arc, fstext.cc:41, but all arcs that enter an HMM
+// state from other states carry the same forward pdf).  Arcs that share destination j AND pdf n form a class c;
+// for the C largest classes (>= kMinClass arcs, as many as fit on chip) the packer factorises the recursions:
+//     A_c(t)      = sum_{arcs in c} alpha'(t,i) w                 one gather per arc          (view 3)
+//     alpha(t+1,j) += A_c(t) x(t,n_c)                              one arc per CLASS           (view 0)
+//     gamma(t,n_c) += A_c(t) beta(t+1,j_c) x(t,n_c)                one arc per CLASS           (view 2)
+//     bx_c(t)      = beta(t+1,j_c) x(t,n_c);  beta'(t,i) += w bx_c one gather per arc          (view 4)
+// The class sums live in an EXTENSION of the state rows (virtual states S_pad .. S_pad+C-1): alpha rows hold
+// [alpha'(t,.) | A_c(t)], spilled and reloaded together, the beta row holds [beta(t+1,.) | bx_c(t)].  Arcs outside the
+// selected classes keep the two-gather records of views 0-2, so a graph with random pdfs packs exactly as before.
+//   view 3 (class pass)   row = class,            a = source state (alpha'),   one operand
+//   view 4 (beta pass 2)  row = source state,     a = S_pad + class (bx),      one operand
+// Rows of view 1 whose state also has arcs in view 4 carry bit 30 in their row code ("add what view 4 left").
 #pragma once
 #include <stdint.h>
 
 namespace chainb200 {
 
 constexpr uint32_t kBlobMagic = 0x42324348u;  // "HC2B"
-constexpr uint32_t kBlobVersion = 9;
+constexpr uint32_t kBlobVersion = 10;
 #ifndef CHAIN_B200_NW
 #define CHAIN_B200_NW 16
 #endif
@@ -49,15 +64,20 @@ struct BlobView {
   int64_t off_split;        // int32 [n_split*3]    {row, first slot, slot count}
 };
 
+constexpr int kNumViews = 5;
+constexpr int32_t kRowExtraFlag = 0x40000000;  // view 1: add the partial result view 4 stored for this row
+
 struct BlobHeader {
   uint32_t magic, version;
   int32_t S, K, D, nwarps, S_pad, D_pad, max_sub, log_domain;
-  int32_t opt_G, reserved[3];  // group width whose bank geometry the column order was optimised for
-  BlobView view[3];
+  int32_t opt_G;               // group width whose bank geometry the column order was optimised for
+  int32_t C, C_pad, R_pad;     // selected (dst,pdf) classes; R_pad = S_pad + C_pad = floats per utterance of a state row
+  BlobView view[kNumViews];
   int64_t off_leaky, off_init, off_final;
+  int64_t off_cls_dst, off_cls_pdf;  // int32 [C_pad] destination state / pdf of each class
   int64_t total_bytes;
-  double predicted_wavefronts[3];  // packer's bank-conflict model for G=4 (per frame, per CTA)
-  double ideal_wavefronts[3];
+  double predicted_wavefronts[kNumViews];  // packer's bank-conflict model (per frame, per CTA)
+  double ideal_wavefronts[kNumViews];
 };
 
 }  // namespace chainb200

@@ -17,7 +17,9 @@ struct DView {
 };
 
 struct DenParams {
-  DView view[3];
+  DView view[kNumViews];
+  const int32_t *cls_dst, *cls_pdf;  // [C_pad] destination state / pdf of every (dst,pdf) class
+  int C, C_pad, R_pad;               // R_pad = S_pad + C_pad: floats per utterance of a state row incl. class sums
   const float *leaky, *init, *fin;
   const float *x;
   const int64_t *lengths;
@@ -116,7 +118,7 @@ inline DenWs den_ws_layout(const BlobHeader &h, int B, int T) {
   DenWs w;
   size_t off = 0;
   const size_t Bp = (size_t)B + 3;
-  w.alpha = off; off = align_up(off + sizeof(float) * Bp * (T + 1) * h.S_pad);
+  w.alpha = off; off = align_up(off + sizeof(float) * Bp * (T + 1) * h.R_pad);
   w.tot = off; off = align_up(off + sizeof(float) * Bp * (T + 1));
   w.logp = off; off = align_up(off + sizeof(float) * Bp);
   w.diag = off; off = align_up(off + sizeof(float) * 2 * Bp);
@@ -125,7 +127,7 @@ inline DenWs den_ws_layout(const BlobHeader &h, int B, int T) {
 }
 
 inline size_t den_smem_bytes(const BlobHeader &h, int G) {
-  return sizeof(float) * ((size_t)2 * h.S_pad * G + (size_t)3 * h.D_pad * G +
+  return sizeof(float) * ((size_t)2 * h.R_pad * G + (size_t)3 * h.D_pad * G +
                           (size_t)h.max_sub * G * (h.log_domain ? 2 : 1)) + 128;
 }
 
@@ -159,7 +161,9 @@ int launch_den_shared_log(const BlobHeader &h, const DenParams &p, int G, bool l
 inline bool records_fit_l1(const BlobHeader &h, size_t smem) {
   // n_recs includes the (never consumed) register-bank run-out of every warp stream
   const int64_t runout = (int64_t)DEN_NW * 3 * kFifoPairs * 64;
-  const size_t recs = (size_t)(h.view[0].n_recs + h.view[1].n_recs + h.view[2].n_recs - 3 * runout) * 8;
+  int64_t n = 0;
+  for (int i = 0; i < kNumViews; i++) n += h.view[i].n_recs - runout;
+  const size_t recs = (size_t)n * 8;
   return recs + smem + 24 * 1024 <= 228 * 1024;
 }
 

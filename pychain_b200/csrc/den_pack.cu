@@ -107,7 +107,7 @@ static void balance_groups(const std::vector<Unit> &units, std::vector<int> &ord
     for (int c = 0; c < 64; c++) sum[c] = hist[first][c];
     const size_t len0 = units[first].arcs.size();
     // bank groups already taken by the output rows of this group (the epilogue stores out[row][g])
-    auto out_group = [&](int u) { const int c = units[u].row_code; return (uint32_t)(c >= 0 ? c : -2 - c) & mask; };
+    auto out_group = [&](int u) { const int c = units[u].row_code; return (uint32_t)(c >= 0 ? (c & 0xfffff) : -2 - c) & mask; };
     unsigned out_used = 1u << out_group(first);
     for (int pick = 1; pick < P && (int)out.size() < n; pick++) {
       int best = -1;
@@ -226,20 +226,39 @@ static void arrange_slice(const std::vector<const Unit *> &lanes, int width, std
   }
 }
 
-static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, const std::vector<uint32_t> &ab,
-                       const float *w, int n_a, int n_b, bool structure_only, bool log_domain, int P, ViewBuild &v) {
+// The arcs of one view: arc k belongs to row row_of[k] and multiplies A[ab & 0xffff] (and B[ab >> 16]) by w.
+struct ArcSet {
+  std::vector<int32_t> row_of;
+  std::vector<uint32_t> ab;
+  std::vector<float> w;
+  void push(int32_t row, uint32_t ab_, float w_) { row_of.push_back(row); ab.push_back(ab_); w.push_back(w_); }
+  int size() const { return (int)row_of.size(); }
+};
+
+// skip_empty: rows without arcs get no unit (views whose epilogue need not run for every row);
+// row_flags: optional per-row bits OR-ed into the row code (kRowExtraFlag).
+static void build_view(int n_rows, const ArcSet &arcs, int n_a, int n_b, bool structure_only, bool log_domain, int P,
+                       bool skip_empty, const std::vector<int32_t> *row_flags, int effort_K, bool one_operand,
+                       ViewBuild &v) {
   v.n_rows = n_rows;
-  const int effort = pack_effort(K);
+  const int K = arcs.size();
+  const std::vector<int32_t> &row_of = arcs.row_of;
+  const std::vector<uint32_t> &ab = arcs.ab;
+  const float *w = arcs.w.data();
+  const int effort = pack_effort(effort_K);
   Rng rng(0xC0FFEEull + (uint64_t)n_rows * 7919u + (uint64_t)K);
   // rows -> arc lists, arc order inside a row = CSR order (the reference's summation order)
   std::vector<int32_t> deg(n_rows, 0);
   for (int k = 0; k < K; k++) deg[row_of[k]]++;
   std::vector<std::vector<Arc>> by_row(n_rows);
   for (int r = 0; r < n_rows; r++) by_row[r].reserve(deg[r]);
-  for (int k = 0; k < K; k++) by_row[row_of[k]].push_back(Arc{ab[k], w ? w[k] : 0.f});
+  for (int k = 0; k < K; k++) by_row[row_of[k]].push_back(Arc{ab[k], w[k]});
+  auto code_of = [&](int r) { return row_flags ? (r | (*row_flags)[r]) : r; };
 
   // split heavy rows so that no lane carries more than `cap` arcs
-  const double mean = (double)K / std::max(1, n_rows);
+  int rows_used = n_rows;
+  if (skip_empty) { rows_used = 0; for (int r = 0; r < n_rows; r++) rows_used += deg[r] > 0; }
+  const double mean = (double)K / std::max(1, rows_used);
   int cap = std::max(32, 4 * (int)(mean + 0.999));
   cap += cap & 1;
   std::vector<Unit> units;
@@ -248,12 +267,13 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
   int n_sub = 0;
   for (int r = 0; r < n_rows; r++) {
     const int d = deg[r];
+    if (d == 0 && skip_empty) continue;
     if (d <= cap) {
-      units.push_back(Unit{r, std::move(by_row[r])});
+      units.push_back(Unit{code_of(r), std::move(by_row[r])});
       continue;
     }
     const int pieces = (d + cap - 1) / cap;
-    v.split.push_back(r); v.split.push_back(n_sub); v.split.push_back(pieces);
+    v.split.push_back(code_of(r)); v.split.push_back(n_sub); v.split.push_back(pieces);
     int pos = 0;
     for (int pc = 0; pc < pieces; pc++) {
       const int len = d / pieces + (pc < d % pieces ? 1 : 0);
@@ -273,7 +293,7 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
   std::stable_sort(order.begin(), order.end(),
                    [&](int x, int y) { return units[x].arcs.size() > units[y].arcs.size(); });
   if (effort >= 1) balance_groups(units, order, P);
-  const int n_slices = ((int)units.size() + 31) / 32;
+  const int n_slices = ((int)units.size() + 31) / 32;   // 0 for an empty view: every warp then runs 0 pairs
   v.n_slices = n_slices;
   v.rows.assign((size_t)n_slices * 32, -1);
   v.width.assign(n_slices, 0);
@@ -333,10 +353,10 @@ static void build_view(int n_rows, int K, const std::vector<int32_t> &row_of, co
           s_ab[s][pos] = ga | (gb << 16);
           ia[q * P + i] = ga; ib[q * P + i] = gb;
         }
-        const int wf = phase_wavefronts(ia + P * q, P, P) + phase_wavefronts(ib + P * q, P, P);
+        const int wf = phase_wavefronts(ia + P * q, P, P) + (one_operand ? 0 : phase_wavefronts(ib + P * q, P, P));
         v.predicted += wf;
         slice_cost[s] += wf;
-        v.ideal += 2;
+        v.ideal += one_operand ? 1 : 2;
       }
     }
   }
@@ -420,31 +440,120 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
   if (fp && bp && !log_domain)
     for (int k = 0; k < Kv; k++)
       if (!(fp[k] >= 0.f) || !(bp[k] >= 0.f)) return CHAIN_B200_ERR_INVALID_ARG;  // probabilities (sign bit is a flag)
-  std::vector<int32_t> row_dst(Kv), row_src(Kv), row_pdf(Kv);
-  std::vector<uint32_t> ab_fwd(Kv), ab_bwd(Kv), ab_gam(Kv);
   for (int k = 0; k < Kv; k++) {
     const int32_t bs = bt[3 * k], bd = bt[3 * k + 1], bn = bt[3 * k + 2];
     const int32_t fs = ft[3 * k], fd = ft[3 * k + 1], fn = ft[3 * k + 2];
     if (bs < 0 || bs >= S || bd < 0 || bd >= S || bn < 0 || bn >= D) return CHAIN_B200_ERR_INVALID_ARG;
     if (fs < 0 || fs >= S || fd < 0 || fd >= S || fn < 0 || fn >= D) return CHAIN_B200_ERR_INVALID_ARG;
-    row_dst[k] = bd; ab_fwd[k] = (uint32_t)bs | ((uint32_t)bn << 16);  // backward-CSR order
-    row_src[k] = fs; ab_bwd[k] = (uint32_t)fd | ((uint32_t)fn << 16);  // forward-CSR order
-    row_pdf[k] = fn; ab_gam[k] = (uint32_t)fs | ((uint32_t)fd << 16);  // forward-CSR order
   }
-  ViewBuild vb[3];
+  const int S_pad = (S + 3) / 4 * 4, D_pad = (D + 3) / 4 * 4;
   const bool so = (out == nullptr);
-  build_view(S, Kv, row_dst, ab_fwd, bp, S, D, so, log_domain, P, vb[0]);
-  build_view(S, Kv, row_src, ab_bwd, fp, S, D, so, log_domain, P, vb[1]);
-  build_view(D, Kv, row_pdf, ab_gam, fp, S, S, so, log_domain, P, vb[2]);
+
+  // ---- (dst, pdf) classes: the arcs of one destination that share a pdf (see den_blob.h) ----------------
+  // candidates in backward-CSR order (arcs grouped by destination), members keep their CSR order
+  struct Cls { int32_t dst, pdf; std::vector<int32_t> arcs; };
+  std::vector<Cls> cls;
+  ViewBuild vb[kNumViews];
+  int C = 0, C_pad = 0, R_pad = S_pad;
+  const int G = (group_width == 1 || group_width == 2) ? group_width : 4;
+  const long chip_floats = (227L * 1024 - 1024) / 4 / G;   // per utterance of a group (den_smem_bytes + static)
+  long c_cap = 65532L - S_pad;
+  for (int attempt = 0;; attempt++) {
+  cls.clear();
+  std::vector<int32_t> cls_of_bwd(Kv, -1);
+  {
+    int min_class = 4;
+    if (const char *e = getenv("CHAIN_B200_MIN_CLASS")) min_class = std::max(2, atoi(e));
+    // room on chip next to 2 state rows + 3 frame rows (+ an allowance for split-row slots) of G utterances
+    long budget = chip_floats - 2L * S_pad - 3L * D_pad - 64;
+    long c_max = std::max(0L, std::min(budget / 2, c_cap)) / 4 * 4;
+    if (const char *e = getenv("CHAIN_B200_MAX_CLASSES")) c_max = std::min(c_max, (long)std::max(0, atoi(e)) / 4 * 4);
+    if (log_domain) c_max = 0;
+    std::vector<Cls> cand;
+    if (c_max > 0) {
+      std::vector<int32_t> idx;
+      for (int s = 0; s < S; s++) {
+        idx.clear();
+        for (int k = bi[2 * s]; k < bi[2 * s + 1]; k++) idx.push_back(k);
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return bt[3 * x + 2] < bt[3 * y + 2]; });
+        for (size_t i = 0; i < idx.size();) {
+          size_t j = i;
+          while (j < idx.size() && bt[3 * idx[j] + 2] == bt[3 * idx[i] + 2]) j++;
+          if ((int)(j - i) >= min_class) {
+            Cls c{s, bt[3 * idx[i] + 2], {}};
+            c.arcs.assign(idx.begin() + i, idx.begin() + j);
+            cand.push_back(std::move(c));
+          }
+          i = j;
+        }
+      }
+      std::stable_sort(cand.begin(), cand.end(), [](const Cls &x, const Cls &y) { return x.arcs.size() > y.arcs.size(); });
+      if ((long)cand.size() > c_max) cand.resize((size_t)c_max);
+    }
+    cls.swap(cand);
+    for (size_t c = 0; c < cls.size(); c++)
+      for (int k : cls[c].arcs) cls_of_bwd[k] = (int32_t)c;
+  }
+  C = (int)cls.size(); C_pad = (C + 3) / 4 * 4; R_pad = S_pad + C_pad;
+  // class of a forward-CSR arc: by (dst, pdf)
+  std::vector<int32_t> cls_of_fwd(Kv, -1);
+  if (C > 0) {
+    std::vector<std::pair<uint64_t, int32_t>> keys(C);
+    for (int c = 0; c < C; c++) keys[c] = {((uint64_t)cls[c].dst << 32) | (uint32_t)cls[c].pdf, c};
+    std::sort(keys.begin(), keys.end());
+    for (int k = 0; k < Kv; k++) {
+      const uint64_t key = ((uint64_t)ft[3 * k + 1] << 32) | (uint32_t)ft[3 * k + 2];
+      auto it = std::lower_bound(keys.begin(), keys.end(), std::make_pair(key, (int32_t)-1));
+      if (it != keys.end() && it->first == key) cls_of_fwd[k] = it->second;
+    }
+  }
+  auto W = [&](const float *p, int k) { return p ? p[k] : 0.f; };
+  const float one = log_domain ? 0.f : 1.f;
+  ArcSet a0, a1, a2, a3, a4;
+  std::vector<int32_t> flags1(S, 0);
+  for (int k = 0; k < Kv; k++) {                       // backward-CSR order: rows = destinations
+    const int32_t src = bt[3 * k], dst = bt[3 * k + 1], pdf = bt[3 * k + 2], c = cls_of_bwd[k];
+    if (c < 0) {
+      a0.push(dst, (uint32_t)src | ((uint32_t)pdf << 16), W(bp, k));
+    } else {
+      if (cls[c].arcs.front() == k) a0.push(dst, (uint32_t)(S_pad + c) | ((uint32_t)pdf << 16), one);  // the class as ONE arc
+      a3.push(c, (uint32_t)src, W(bp, k));             // its members: one operand each
+    }
+  }
+  for (int k = 0; k < Kv; k++) {                       // forward-CSR order: rows = sources / pdfs
+    const int32_t src = ft[3 * k], dst = ft[3 * k + 1], pdf = ft[3 * k + 2], c = cls_of_fwd[k];
+    if (c < 0) {
+      a1.push(src, (uint32_t)dst | ((uint32_t)pdf << 16), W(fp, k));
+      a2.push(pdf, (uint32_t)src | ((uint32_t)dst << 16), W(fp, k));
+    } else {
+      a4.push(src, (uint32_t)(S_pad + c), W(fp, k));
+      flags1[src] = kRowExtraFlag;
+    }
+  }
+  for (int c = 0; c < C; c++) a2.push(cls[c].pdf, (uint32_t)(S_pad + c) | ((uint32_t)cls[c].dst << 16), one);
+  for (int i = 0; i < kNumViews; i++) vb[i] = ViewBuild();
+  build_view(S, a0, R_pad, D, so, log_domain, P, false, nullptr, Kv, false, vb[0]);
+  build_view(S, a1, S, D, so, log_domain, P, false, C > 0 ? &flags1 : nullptr, Kv, false, vb[1]);
+  build_view(D, a2, R_pad, S, so, log_domain, P, false, nullptr, Kv, false, vb[2]);
+  build_view(std::max(C, 1), a3, S, 1, so, log_domain, P, true, nullptr, Kv, true, vb[3]);
+  build_view(S, a4, R_pad, 1, so, log_domain, P, true, nullptr, Kv, true, vb[4]);
+  // split-row slots share the chip with the class sums: give classes back until everything fits
+  int max_sub = 0;
+  for (int i = 0; i < kNumViews; i++) max_sub = std::max(max_sub, vb[i].n_sub);
+  const long need = 2L * R_pad + 3L * D_pad + max_sub;
+  if (C == 0 || need <= chip_floats || attempt >= 4) break;
+  c_cap = std::max(0L, (long)C - ((need - chip_floats + 1) / 2 + 4));
+  }
 
   BlobHeader h;
   memset(&h, 0, sizeof(h));
   h.magic = kBlobMagic; h.version = kBlobVersion;
   h.S = S; h.K = Kv; h.D = D; h.nwarps = DEN_NW; h.log_domain = log_domain ? 1 : 0;
   h.opt_G = 32 / P;
-  h.S_pad = (S + 3) / 4 * 4; h.D_pad = (D + 3) / 4 * 4;
+  h.S_pad = S_pad; h.D_pad = D_pad;
+  h.C = C; h.C_pad = C_pad; h.R_pad = R_pad;
   size_t off = align_up(sizeof(BlobHeader));
-  for (int i = 0; i < 3; i++) {
+  for (int i = 0; i < kNumViews; i++) {
     BlobView &bv = h.view[i];
     const ViewBuild &b = vb[i];
     bv.n_rows = b.n_rows; bv.n_slices = b.n_slices; bv.n_split = b.n_split; bv.n_sub = b.n_sub;
@@ -460,13 +569,19 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
   h.off_leaky = (int64_t)off; off = align_up(off + (size_t)h.S_pad * 4);
   h.off_init = (int64_t)off; off = align_up(off + (size_t)h.S_pad * 4);
   h.off_final = (int64_t)off; off = align_up(off + (size_t)h.S_pad * 4);
+  h.off_cls_dst = (int64_t)off; off = align_up(off + (size_t)C_pad * 4 + 4);
+  h.off_cls_pdf = (int64_t)off; off = align_up(off + (size_t)C_pad * 4 + 4);
   h.total_bytes = (int64_t)off;
   if (!out) return h.total_bytes;
   if (out_bytes < h.total_bytes || !fp || !bp || (!leaky && !log_domain) || !init || !fin) return CHAIN_B200_ERR_INVALID_ARG;
   char *base = (char *)out;
   memset(base, 0, (size_t)h.total_bytes);
   memcpy(base, &h, sizeof(h));
-  for (int i = 0; i < 3; i++) {
+  for (int c = 0; c < C; c++) {
+    ((int32_t *)(base + h.off_cls_dst))[c] = cls[c].dst;
+    ((int32_t *)(base + h.off_cls_pdf))[c] = cls[c].pdf;
+  }
+  for (int i = 0; i < kNumViews; i++) {
     const BlobView &bv = h.view[i];
     const ViewBuild &b = vb[i];
     memcpy(base + bv.off_warp_info, b.warp_info.data(), b.warp_info.size() * 8);

@@ -55,6 +55,23 @@ __device__ __forceinline__ void consume_rec(const uint32_t ab, const float w, co
   }
 }
 
+// Record pairs per register bank of the two-operand passes.  At G = 4 a pair in flight holds 16 operand registers
+// next to the two banks, and with kFifoPairs = 4 ptxas spills bank entries right after their loads (which serialises
+// the warp on the L2 latency); one pair less keeps the loop spill-free.
+#ifndef CHAIN_B200_NF2_G4
+#define CHAIN_B200_NF2_G4 (kFifoPairs - 1)
+#endif
+template <int G> __host__ __device__ constexpr int nf2() { return G == 4 ? CHAIN_B200_NF2_G4 : kFifoPairs; }
+
+// One-operand record (class views 3 and 4): acc += A[a] * w.
+template <int G>
+__device__ __forceinline__ void consume_rec1(const uint32_t ab, const float w, const float *__restrict__ A, float (&acc)[G]) {
+  float a[G];
+  ld_vec<G>(A + (ab & 0xffffu) * G, a);
+#pragma unroll
+  for (int g = 0; g < G; g++) acc[g] = fmaf(a[g], w, acc[g]);
+}
+
 // One SELL pass: every lane owns one row (or sub-row) of each of its warp's slices and
 // accumulates sum_k w_k * A[a_k][g] * Bv[b_k][g] over the row's records.  The warp's
 // records are one contiguous stream consumed in pairs by a flat counted loop.  Two register
@@ -63,27 +80,34 @@ __device__ __forceinline__ void consume_rec(const uint32_t ab, const float w, co
 // flight to cover the L2 latency and no load ever lands in a register that is still live.
 // The sign bit of the second weight of a pair ends a slice: run the epilogue for the lane's
 // row and move to the next row code (fetched two slices ahead).
-template <int G, bool L1C, class Epi>
+// ONE: the records carry one operand (consume_rec1), Bv is unused.  NF: record pairs per register bank (<= NF,
+// the depth the streams' run-out is padded for); the gamma pass of G = 4 has the heaviest epilogue and runs one short.
+template <int G, bool L1C, bool ONE, int NF, class Epi>
 __device__ __forceinline__ void sell_pass(const DView &v, const float *__restrict__ A, const float *__restrict__ Bv,
                                           float *__restrict__ partial, int warp, int lane, Epi &epi) {
   const uint2 *sp = v.recs + v.warp_info[3 * warp] + lane;
   const int npairs = (int)v.warp_info[3 * warp + 1];
   const int32_t *rp = v.rows + v.warp_info[3 * warp + 2] + lane;
-  uint2 fa[kFifoPairs][2], fb[kFifoPairs][2];
+  uint2 fa[NF][2], fb[NF][2];
 #pragma unroll
-  for (int d = 0; d < kFifoPairs; d++) {
+  for (int d = 0; d < NF; d++) {
     fa[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
     fa[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
   }
-  sp += 2 * kFifoPairs * 32;
+  sp += 2 * NF * 32;
   int row = __ldg(rp), row_n1 = __ldg(rp + 32), row_n2 = __ldg(rp + 64);
   rp += 96;
   float acc[G];
 #pragma unroll
   for (int g = 0; g < G; g++) acc[g] = 0.f;
   auto process = [&](const uint2 r0, const uint2 r1) {
-    consume_rec<G>(r0.x, __uint_as_float(r0.y), A, Bv, acc);
-    consume_rec<G>(r1.x, __uint_as_float(r1.y & 0x7fffffffu), A, Bv, acc);
+    if constexpr (ONE) {
+      consume_rec1<G>(r0.x, __uint_as_float(r0.y), A, acc);
+      consume_rec1<G>(r1.x, __uint_as_float(r1.y & 0x7fffffffu), A, acc);
+    } else {
+      consume_rec<G>(r0.x, __uint_as_float(r0.y), A, Bv, acc);
+      consume_rec<G>(r1.x, __uint_as_float(r1.y & 0x7fffffffu), A, Bv, acc);
+    }
     if (r1.y & 0x80000000u) {  // warp-uniform: last pair of the slice
       if (row >= 0) epi(row, acc);
       else if (row <= -2) st_vec<G>(partial + (size_t)(-2 - row) * G, acc);
@@ -96,40 +120,40 @@ __device__ __forceinline__ void sell_pass(const DView &v, const float *__restric
     }
   };
   int j = 0;
-  for (; j + 2 * kFifoPairs <= npairs; j += 2 * kFifoPairs) {  // full double banks: straight-line code
+  for (; j + 2 * NF <= npairs; j += 2 * NF) {  // full double banks: straight-line code
 #pragma unroll
-    for (int d = 0; d < kFifoPairs; d++) {
+    for (int d = 0; d < NF; d++) {
       fb[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
       fb[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
     }
-    sp += 2 * kFifoPairs * 32;
+    sp += 2 * NF * 32;
 #pragma unroll
-    for (int d = 0; d < kFifoPairs; d++) process(fa[d][0], fa[d][1]);
+    for (int d = 0; d < NF; d++) process(fa[d][0], fa[d][1]);
 #pragma unroll
-    for (int d = 0; d < kFifoPairs; d++) {
+    for (int d = 0; d < NF; d++) {
       fa[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
       fa[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
     }
-    sp += 2 * kFifoPairs * 32;
+    sp += 2 * NF * 32;
 #pragma unroll
-    for (int d = 0; d < kFifoPairs; d++) process(fb[d][0], fb[d][1]);
+    for (int d = 0; d < NF; d++) process(fb[d][0], fb[d][1]);
   }
-  const int rem = npairs - j;  // < 2*kFifoPairs pairs left: bank A holds the first kFifoPairs of them
+  const int rem = npairs - j;  // < 2*NF pairs left: bank A holds the first NF of them
   if (rem > 0) {
-    if (rem > kFifoPairs) {
+    if (rem > NF) {
 #pragma unroll
-      for (int d = 0; d < kFifoPairs; d++) {
+      for (int d = 0; d < NF; d++) {
         fb[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
         fb[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
       }
     }
 #pragma unroll
-    for (int d = 0; d < kFifoPairs; d++)
+    for (int d = 0; d < NF; d++)
       if (d < rem) process(fa[d][0], fa[d][1]);
-    if (rem > kFifoPairs) {
+    if (rem > NF) {
 #pragma unroll
-      for (int d = 0; d < kFifoPairs; d++)
-        if (kFifoPairs + d < rem) process(fb[d][0], fb[d][1]);
+      for (int d = 0; d < NF; d++)
+        if (NF + d < rem) process(fb[d][0], fb[d][1]);
     }
   }
 }
@@ -161,13 +185,17 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
   __shared__ __align__(8) unsigned long long mbar[2];  // 0: alpha rows, 1: x frames
   __shared__ float red[DEN_NW * 4];
   __shared__ float red2[DEN_NW * 4];
+  __shared__ double logp_s[4];
+  __shared__ float invz_s[4];
+  __shared__ int Lg[4];
 
   const int S = p.S, D = p.D, T = p.T, S_pad = p.S_pad, D_pad = p.D_pad;
+  const int R_pad = p.R_pad, C = p.C;   // a state row = [S_pad states | C_pad class sums] x G utterances
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float c = p.coeff;
   float *buf0 = reinterpret_cast<float *>(smem_raw);
-  float *buf1 = buf0 + (size_t)S_pad * G;
-  float *x_s = buf1 + (size_t)S_pad * G;
+  float *buf1 = buf0 + (size_t)R_pad * G;
+  float *x_s = buf1 + (size_t)R_pad * G;
   float *xraw = x_s + (size_t)D_pad * G;
   float *gam_s = xraw + (size_t)D_pad * G;
   float *partial = gam_s + (size_t)D_pad * G;
@@ -177,18 +205,8 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
   const bool clamp_x = (p.flags & CHAIN_B200_CLAMP_X) && !(p.flags & CHAIN_B200_X_IS_EXP);
   const bool exp_x = !(p.flags & CHAIN_B200_X_IS_EXP);
 
-  // every CTA streams the same packed records every frame; spreading the CTAs over n_rep
-  // identical copies keeps them from queueing on the same L2 lines at the same time
-  DView views[3];
-  {
-    const size_t rep_off = (size_t)(blockIdx.x % p.n_rep) * p.rep_stride;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      views[i] = p.view[i];
-      views[i].recs = reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(p.view[i].recs) + rep_off);
-      views[i].rows = reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(p.view[i].rows) + rep_off);
-    }
-  }
+  // the packed views are read straight from the kernel parameters (constant bank): no registers held
+  const DView *views = p.view;
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
@@ -207,19 +225,18 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
 
   for (int gi = blockIdx.x; gi < p.num_groups; gi += gridDim.x) {
     const int b0 = gi * G;
-    int Lg[G];
+    // lengths of the group's utterances: shared memory (read where needed), not registers held for the whole recursion
     int Lmax = 0;
 #pragma unroll
     for (int g = 0; g < G; g++) {
       long long l = (b0 + g < p.B) ? p.lengths[b0 + g] : 0;
-      Lg[g] = (int)(l < 0 ? 0 : (l > T ? T : l));
-      Lmax = max(Lmax, Lg[g]);
+      const int lx = (int)(l < 0 ? 0 : (l > T ? T : l));
+      if (tid == 0) Lg[g] = lx;
+      Lmax = max(Lmax, lx);
     }
-    float *aws = p.alpha_ws + (size_t)gi * (T + 1) * S_pad * G;
+    float *aws = p.alpha_ws + (size_t)gi * (T + 1) * R_pad * G;
     float *tws = p.tot_ws + (size_t)gi * (T + 1) * G;
-    const float *xg[G];
-#pragma unroll
-    for (int g = 0; g < G; g++) xg[g] = p.x + (size_t)min(b0 + g, p.B - 1) * T * D;
+    auto xrow = [&](int g, int f) { return p.x + ((size_t)min(b0 + g, p.B - 1) * T + f) * D; };  // frame f of utterance g
 
     // stage one frame of x: TMA bulk copies into xraw (one per live utterance) ...
     auto issue_x = [&](int f) {
@@ -232,11 +249,13 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         mbar_expect_tx(&mbar[1], bytes);
 #pragma unroll
         for (int g = 0; g < G; g++)
-          if (f < Lg[g]) tma_load_1d(xraw + (size_t)g * D_pad, xg[g] + (size_t)f * D, (uint32_t)D * 4u, &mbar[1]);
+          if (f < Lg[g]) tma_load_1d(xraw + (size_t)g * D_pad, xrow(g, f), (uint32_t)D * 4u, &mbar[1]);
       }
     };
-    // ... then clamp / exp while transposing into the interleaved x_s[pdf][g]; dead lanes get 0
-    auto transform_x = [&](int f) {
+    // ... then clamp / exp while transposing into the interleaved x_s[pdf][g]; dead lanes get 0.  The frame's
+    // normaliser 1/tot(f) is folded in here (every use of x(f,.) is divided by tot(f): chain-computation.cc:150-173,
+    // 289-309), so no epilogue multiplies by it and it is not held in registers across a pass.
+    auto transform_x = [&](int f, const float (&sc)[G]) {
       if (p.use_tma_x) { mbar_wait(&mbar[1], ph_x); ph_x ^= 1u; }
       for (int n = tid; n < D; n += DEN_NT) {
         float v[G];
@@ -244,9 +263,10 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         for (int g = 0; g < G; g++) {
           float t = 0.f;
           if (f < Lg[g]) {
-            t = p.use_tma_x ? xraw[(size_t)g * D_pad + n] : __ldg(xg[g] + (size_t)f * D + n);
+            t = p.use_tma_x ? xraw[(size_t)g * D_pad + n] : __ldg(xrow(g, f) + n);
             if (clamp_x) t = clampf(t, kClampLo, kClampHi);
             if (exp_x) t = expf(t);
+            t *= sc[g];
           }
           v[g] = t;
         }
@@ -254,10 +274,14 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       }
     };
 
-    double logp[G];
-    float invZ[G], tot[G];
+    double *logp = logp_s;  // only thread 0 accumulates the log-likelihoods (shared memory: no registers held)
+    float *invZ = invz_s;   // 1/Z per utterance: written once in the forward pass, read when an utterance enters the backward pass
+    float inv[G];   // 1/tot of the frame about to be staged; dead during the passes
 #pragma unroll
-    for (int g = 0; g < G; g++) { logp[g] = 0.0; invZ[g] = 0.f; }
+    for (int g = 0; g < G; g++) {
+      if (tid == 0) { logp[g] = 0.0; invZ[g] = 0.f; }
+      inv[g] = tot0 > 0.f ? 1.0f / tot0 : 0.f;
+    }
 
     // ============================================================ forward
     float *A = buf0, *Bn = buf1;  // A: alpha'(t-1) (read), Bn: alpha(t) (written)
@@ -267,7 +291,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
     {
       bool need_z = false;
 #pragma unroll
-      for (int g = 0; g < G; g++) { tot[g] = tot0; need_z |= (Lg[g] == 0); }
+      for (int g = 0; g < G; g++) need_z |= (Lg[g] == 0);
       float zp[G];
 #pragma unroll
       for (int g = 0; g < G; g++) zp[g] = 0.f;
@@ -291,25 +315,35 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         block_sum_vec<G>(zp, red2);
 #pragma unroll
         for (int g = 0; g < G; g++)
-          if (Lg[g] == 0) { invZ[g] = 1.0f / zp[g]; logp[g] += (double)logf(zp[g]); }
+          if (Lg[g] == 0 && tid == 0) { invZ[g] = 1.0f / zp[g]; logp[g] += (double)logf(zp[g]); }
       }
     }
     __syncthreads();
 
     for (int t = 1; t <= Lmax; t++) {
-      transform_x(t - 1);
-      __syncthreads();  // x_s complete, xraw free
+      transform_x(t - 1, inv);   // x(t-1,.) / tot(t-1)
+      if (C) {
+        // class sums A_c(t-1) = sum_{arcs of class c} alpha'(t-1,src) * w: one operand per arc.  They extend the
+        // state row (virtual states S_pad + c) and are spilled with it: the backward pass needs them again.
+        float *aext = A + (size_t)S_pad * G, *wext = aws + ((size_t)(t - 1) * R_pad + S_pad) * G;
+        auto epi_cls = [&](int row, const float (&acc)[G]) {
+          st_vec<G>(aext + (size_t)row * G, acc);
+          st_vec<G>(wext + (size_t)row * G, acc);
+        };
+        sell_pass<G, L1C, true, kFifoPairs>(views[3], A, nullptr, partial, warp, lane, epi_cls);
+        if (p.view[3].n_split) { __syncthreads(); fixup_split<G>(p.view[3], partial, epi_cls); }
+      }
+      __syncthreads();  // x_s complete, xraw free, class sums complete
       if (t < Lmax) issue_x(t);
-      float inv[G], part[G];
+      float part[G];
 #pragma unroll
-      for (int g = 0; g < G; g++) { inv[g] = tot[g] > 0.f ? 1.0f / tot[g] : 0.f; part[g] = 0.f; }
+      for (int g = 0; g < G; g++) part[g] = 0.f;
       auto epi_fwd = [&](int row, const float (&acc)[G]) {
-        float o[G];
 #pragma unroll
-        for (int g = 0; g < G; g++) { o[g] = acc[g] * inv[g]; part[g] += o[g]; }
-        st_vec<G>(Bn + (size_t)row * G, o);
+        for (int g = 0; g < G; g++) part[g] += acc[g];
+        st_vec<G>(Bn + (size_t)row * G, acc);
       };
-      sell_pass<G, L1C>(views[0], A, x_s, partial, warp, lane, epi_fwd);
+      sell_pass<G, L1C, false, nf2<G>()>(views[0], A, x_s, partial, warp, lane, epi_fwd);
       if (p.view[0].n_split) { __syncthreads(); fixup_split<G>(p.view[0], partial, epi_fwd); }
 #pragma unroll
       for (int g = 0; g < G; g++) {
@@ -323,10 +357,11 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       for (int g = 0; g < G; g++) {
         float s = 0.f;
         for (int w = 0; w < DEN_NW; w++) s += red[w * G + g];
-        tot[g] = s; ct[g] = c * s; zp[g] = 0.f;
+        ct[g] = c * s; zp[g] = 0.f;   // ct = c * tot(t)
+        inv[g] = s > 0.f ? 1.0f / s : 0.f;
         need_z |= (Lg[g] == t);
       }
-      float *awt = aws + (size_t)t * S_pad * G;
+      float *awt = aws + (size_t)t * R_pad * G;
       for (int i = tid; i < S; i += DEN_NT) {
         float v[G];
         ld_vec<G>(Bn + (size_t)i * G, v);
@@ -340,14 +375,19 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       if (tid == 0) {
         float tv[G];
 #pragma unroll
-        for (int g = 0; g < G; g++) { tv[g] = tot[g]; if (t < Lg[g]) logp[g] += (double)logf(tot[g]); }
+        for (int g = 0; g < G; g++) {
+          float s = 0.f;
+          for (int w = 0; w < DEN_NW; w++) s += red[w * G + g];   // tot(t), same order as above
+          tv[g] = s;
+          if (t < Lg[g]) logp[g] += (double)logf(s);
+        }
         st_vec<G>(tws + (size_t)t * G, tv);
       }
       if (need_z) {
         block_sum_vec<G>(zp, red2);
 #pragma unroll
         for (int g = 0; g < G; g++)
-          if (Lg[g] == t) { invZ[g] = 1.0f / zp[g]; logp[g] += (double)logf(zp[g]); }
+          if (Lg[g] == t && tid == 0) { invZ[g] = 1.0f / zp[g]; logp[g] += (double)logf(zp[g]); }
       }
       float *tmp = A; A = Bn; Bn = tmp;
       __syncthreads();
@@ -361,6 +401,8 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
     // ============================================================ backward
     // P: alpha'(t) (TMA-loaded), Q: beta(t+1).  Both forward buffers are free now.
     float *P = buf0, *Q = buf1;
+    // the alpha rows were written with ordinary stores and come back through the async proxy (TMA)
+    asm volatile("fence.proxy.async.global;" ::: "memory");
     for (int i = tid; i < S_pad * G; i += DEN_NT) Q[i] = 0.f;
     if (Lmax > 0) issue_x(Lmax - 1);
     __syncthreads();
@@ -371,8 +413,8 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       for (int g = 0; g < G; g++) inject |= (Lg[g] == t + 1);
       if (tid == 0) {
         fence_proxy_async();
-        mbar_expect_tx(&mbar[0], (uint32_t)S_pad * G * 4u);
-        tma_load_1d(P, aws + (size_t)t * S_pad * G, (uint32_t)S_pad * G * 4u, &mbar[0]);
+        mbar_expect_tx(&mbar[0], (uint32_t)R_pad * G * 4u);   // [alpha'(t) | class sums A_c(t)]
+        tma_load_1d(P, aws + (size_t)t * R_pad * G, (uint32_t)R_pad * G * 4u, &mbar[0]);
       }
       if (inject) {
         for (int i = tid; i < S; i += DEN_NT) {
@@ -385,51 +427,67 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
           st_vec<G>(Q + (size_t)i * G, v);
         }
       }
-      transform_x(t);
-      float inv[G];
       {
         float tv[G];
         ld_vec<G>(tws + (size_t)t * G, tv);
 #pragma unroll
         for (int g = 0; g < G; g++) inv[g] = (t < Lg[g] && tv[g] > 0.f) ? 1.0f / tv[g] : 0.f;
       }
+      transform_x(t, inv);   // x(t,.) / tot(t)
       mbar_wait(&mbar[0], ph_a); ph_a ^= 1u;
       __syncthreads();  // P, Q, x_s ready; xraw free
       if (t > 0) issue_x(t - 1);
+      // bx_c = beta(t+1, dst_c) * x(t, pdf_c) per class, next to beta in the Q row (read by view 4 below)
+      for (int k = tid; k < C; k += DEN_NT) {
+        float q[G], xv[G];
+        ld_vec<G>(Q + (size_t)__ldg(p.cls_dst + k) * G, q);
+        ld_vec<G>(x_s + (size_t)__ldg(p.cls_pdf + k) * G, xv);
+#pragma unroll
+        for (int g = 0; g < G; g++) q[g] *= xv[g];
+        st_vec<G>(Q + (size_t)(S_pad + k) * G, q);
+      }
 
       // ---- gamma pass: rows = pdfs; gamma(t,n) = x(t,n)/tot(t) * sum alpha'(src) p beta(dst)
-      float gsum[G];
-#pragma unroll
-      for (int g = 0; g < G; g++) gsum[g] = 0.f;
       auto epi_gam = [&](int row, const float (&acc)[G]) {
         float xv[G], o[G];
         ld_vec<G>(x_s + (size_t)row * G, xv);
 #pragma unroll
-        for (int g = 0; g < G; g++) { o[g] = acc[g] * xv[g] * inv[g]; gsum[g] += o[g]; }
+        for (int g = 0; g < G; g++) o[g] = acc[g] * xv[g];
         st_vec<G>(gam_s + (size_t)row * G, o);
       };
-      sell_pass<G, L1C>(views[2], P, Q, partial, warp, lane, epi_gam);
+      sell_pass<G, L1C, false, nf2<G>()>(views[2], P, Q, partial, warp, lane, epi_gam);
       if (p.view[2].n_split) { __syncthreads(); fixup_split<G>(p.view[2], partial, epi_gam); }
-      __syncthreads();  // gamma rows complete; everybody done reading P
+      __syncthreads();  // gamma rows complete; everybody done reading P; bx complete
+
+      // ---- beta' pass, class arcs: rows = source states, one operand (bx_c) per arc; the raw sums wait in P
+      if (C) {
+        auto epi_b2 = [&](int row, const float (&acc)[G]) { st_vec<G>(P + (size_t)row * G, acc); };
+        sell_pass<G, L1C, true, kFifoPairs>(views[4], Q, nullptr, partial, warp, lane, epi_b2);
+        if (p.view[4].n_split) { __syncthreads(); fixup_split<G>(p.view[4], partial, epi_b2); }
+        __syncthreads();
+      }
 
       // ---- beta' pass: rows = source states; beta'(t,i) = sum p beta(t+1,dst) x(t,pdf) / tot(t)
-      float lpart[G], ab[G];
+      float lpart[G];
 #pragma unroll
-      for (int g = 0; g < G; g++) { lpart[g] = 0.f; ab[g] = 0.f; }
-      auto epi_bwd = [&](int row, const float (&acc)[G]) {
+      for (int g = 0; g < G; g++) lpart[g] = 0.f;
+      auto epi_bwd = [&](int code, const float (&acc)[G]) {
+        const int row = code & (kRowExtraFlag - 1);
         float o[G];
-        const float l = __ldg(lk + row);
-        if (t == 0) {
-          float av[G];
-          ld_vec<G>(P + (size_t)row * G, av);
 #pragma unroll
-          for (int g = 0; g < G; g++) ab[g] = fmaf(av[g], acc[g] * inv[g], ab[g]);
+        for (int g = 0; g < G; g++) o[g] = acc[g];
+        if (code & kRowExtraFlag) {  // this state also has class arcs: view 4 left their sum in P[row]
+          float e[G];
+          ld_vec<G>(P + (size_t)row * G, e);
+#pragma unroll
+          for (int g = 0; g < G; g++) o[g] += e[g];
         }
+        const float l = __ldg(lk + row);
 #pragma unroll
-        for (int g = 0; g < G; g++) { o[g] = acc[g] * inv[g]; lpart[g] = fmaf(o[g], l, lpart[g]); }
+        for (int g = 0; g < G; g++) lpart[g] = fmaf(o[g], l, lpart[g]);
         st_vec<G>(P + (size_t)row * G, o);
       };
-      sell_pass<G, L1C>(views[1], Q, x_s, partial, warp, lane, epi_bwd);
+      sell_pass<G, L1C, false, nf2<G>()>(views[1], Q, x_s, partial, warp, lane, epi_bwd);
       if (p.view[1].n_split) { __syncthreads(); fixup_split<G>(p.view[1], partial, epi_bwd); }
 #pragma unroll
       for (int g = 0; g < G; g++) {
@@ -437,12 +495,17 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         if (lane == 0) red[warp * G + g] = lpart[g];
       }
       // write this frame's gradient rows (coalesced over pdfs) while the other warps finish
+      float gsum[G], ab[G];  // the reference's frame-0 self-check sums (chain-computation.cc:363-371)
+#pragma unroll
+      for (int g = 0; g < G; g++) { gsum[g] = 0.f; ab[g] = 0.f; }
       for (int n = tid; n < D; n += DEN_NT) {  // one vector read per pdf, G coalesced row writes
         float v[G];
         ld_vec<G>(gam_s + (size_t)n * G, v);
 #pragma unroll
-        for (int g = 0; g < G; g++)
+        for (int g = 0; g < G; g++) {
           if (b0 + g < p.B) p.grad[((size_t)(b0 + g) * T + t) * D + n] = (t < Lg[g]) ? v[g] : 0.f;
+          gsum[g] += v[g];
+        }
       }
       __syncthreads();  // beta' rows + partials visible; everybody done reading Q and gam_s
       float cb[G];
@@ -455,11 +518,16 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       for (int i = tid; i < S; i += DEN_NT) {
         float v[G];
         ld_vec<G>(P + (size_t)i * G, v);
+        if (t == 0) {  // alpha'(0,i) = init_i + c * tot(0) * leaky_i (the same for every utterance) times beta'(0,i)
+          const float av = fmaf(c * tot0, __ldg(lk + i), __ldg(ini + i));
+#pragma unroll
+          for (int g = 0; g < G; g++) ab[g] = fmaf(av, v[g], ab[g]);
+        }
 #pragma unroll
         for (int g = 0; g < G; g++) v[g] += cb[g];
         st_vec<G>(P + (size_t)i * G, v);
       }
-      if (t == 0) {  // the reference's self-check quantities (chain-computation.cc:363-371)
+      if (t == 0) {
         block_sum_vec<G>(ab, red2);
         block_sum_vec<G>(gsum, red2);
         if (tid == 0) {
@@ -480,6 +548,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       const size_t n = (size_t)(T - Lmax) * D;
       for (size_t i = tid; i < n; i += DEN_NT) gr[i] = 0.f;
     }
+    __syncthreads();  // Lg / invZ / logp (shared memory) are rewritten at the top of the next group
   }
 }
 
@@ -495,7 +564,8 @@ int chain_b200_den_group_width(int S, int D, int B, int device) {
   BlobHeader h;
   memset(&h, 0, sizeof(h));
   h.S_pad = (S + 3) / 4 * 4; h.D_pad = (D + 3) / 4 * 4;
-  h.max_sub = 256;  // allowance for split rows, unknown before packing
+  h.R_pad = h.S_pad;  // classes only use the room that is left
+  h.max_sub = 256;    // allowance for split rows, unknown before packing
   int num_sms = 148;
   if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) num_sms = 148;
   return choose_G(h, B, num_sms);
@@ -533,7 +603,7 @@ int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev,
   char *base = (char *)ws;
 
   DenParams p;
-  for (int i = 0; i < 3; i++) {
+  for (int i = 0; i < kNumViews; i++) {
     const BlobView &bv = h.view[i];
     p.view[i].warp_info = (const int64_t *)(bd + bv.off_warp_info);
     p.view[i].rows = (const int32_t *)(bd + bv.off_rows);
@@ -541,6 +611,9 @@ int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev,
     p.view[i].split = (const int32_t *)(bd + bv.off_split);
     p.view[i].n_split = bv.n_split;
   }
+  p.cls_dst = (const int32_t *)(bd + h.off_cls_dst);
+  p.cls_pdf = (const int32_t *)(bd + h.off_cls_pdf);
+  p.C = h.C; p.C_pad = h.C_pad; p.R_pad = h.R_pad;
   p.leaky = (const float *)(bd + h.off_leaky);
   p.init = (const float *)(bd + h.off_init);
   p.fin = (const float *)(bd + h.off_final);

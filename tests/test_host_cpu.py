@@ -136,9 +136,9 @@ def test_graph_batch_layouts_and_reorder():
 
 def _parse_blob(blob):
     h = blob.numpy().tobytes()
-    magic, version, S, K, D, nw, S_pad, D_pad, max_sub, _, opt_g, _, _, _ = struct.unpack_from("<II12i", h, 0)
+    magic, version, S, K, D, nw, S_pad, D_pad, max_sub, _, opt_g, C, C_pad, R_pad = struct.unpack_from("<II12i", h, 0)
     views, off = [], 56
-    for i in range(3):
+    for i in range(5):
         n_rows, n_slices, n_split, n_sub, n_recs, o_info, o_rows, o_recs, o_split = struct.unpack_from("<4i5q", h, off)
         off += 56
         info = np.frombuffer(h, np.int64, nw * 3, o_info).reshape(nw, 3)
@@ -146,10 +146,13 @@ def _parse_blob(blob):
         recs = np.frombuffer(h, np.uint32, n_recs * 2, o_recs).reshape(-1, 2)
         split = np.frombuffer(h, np.int32, n_split * 3, o_split).reshape(-1, 3)
         views.append(dict(n_rows=n_rows, n_slices=n_slices, n_sub=n_sub, info=info, rows=rows, recs=recs, split=split))
-    o_leaky, o_init, o_final, total = struct.unpack_from("<4q", h, off)
-    pred = struct.unpack_from("<6d", h, off + 32)
-    return dict(S=S, K=K, D=D, nw=nw, max_sub=max_sub, views=views, total=total, pred=pred,
-                leaky=np.frombuffer(h, np.float32, S, o_leaky), final=np.frombuffer(h, np.float32, S, o_final))
+    o_leaky, o_init, o_final, o_cd, o_cp, total = struct.unpack_from("<6q", h, off)
+    pred = struct.unpack_from("<10d", h, off + 48)
+    return dict(S=S, K=K, D=D, nw=nw, max_sub=max_sub, views=views, total=total, pred=pred, C=C, C_pad=C_pad,
+                S_pad=S_pad, R_pad=R_pad, version=version,
+                cls_dst=np.frombuffer(h, np.int32, C, o_cd), cls_pdf=np.frombuffer(h, np.int32, C, o_cp),
+                leaky=np.frombuffer(h, np.float32, S, o_leaky), final=np.frombuffer(h, np.float32, S, o_final),
+                init=np.frombuffer(h, np.float32, S, o_init))
 
 
 def _decode_view(v, nw):
@@ -181,7 +184,7 @@ def _decode_view(v, nw):
                         slices_seen += 1
                         for lane in range(32):
                             code = int(codes[lane])
-                            row = code if code >= 0 else (sub_owner[-2 - code] if code <= -2 else None)
+                            row = (code & 0xfffff) if code >= 0 else ((sub_owner[-2 - code] & 0xfffff) if code <= -2 else None)
                             assert row is not None or not pending[lane]
                             out += [(row,) + t for t in pending[lane]]
                             pending[lane] = []
@@ -191,14 +194,16 @@ def _decode_view(v, nw):
 
 
 @pytest.mark.parametrize("variant,S,K,D", [("uniform", 70, 400, 24), ("skew", 90, 1500, 16)])
-def test_den_packer_is_lossless(variant, S, K, D):
+def test_den_packer_is_lossless(variant, S, K, D, monkeypatch):
     g = ChainGraph(synth.random_den_fst(S, K, D, seed=9, variant=variant))
     gb = ChainGraphBatch(g, 2)
     gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_PROB)
     engine._prepared_cache.clear()
+    monkeypatch.setenv("CHAIN_B200_MAX_CLASSES", "0")   # the arc-per-record packing (classes: next test)
     prep = engine.prepare_den_graph(gt, g.num_states, D, "cpu")
     b = _parse_blob(prep.blob_host)
     assert (b["S"], b["K"], b["D"], b["nw"]) == (S, K, D, 16) and b["total"] == prep.blob_host.numel()
+    assert b["C"] == 0 and b["R_pad"] == b["S_pad"]
     ft, fp = g.forward_transitions.numpy(), g.forward_transition_probs.numpy()
     want = [
         sorted((int(d), int(s), int(n), np.float32(p)) for (s, d, n), p in zip(ft, fp)),   # alpha: row=dst, a=src, b=pdf
@@ -214,7 +219,7 @@ def test_den_packer_is_lossless(variant, S, K, D):
         assert b["views"][0]["n_sub"] > 0 and b["max_sub"] >= b["views"][0]["n_sub"]
     assert np.array_equal(b["leaky"], g.leaky_probs.numpy())
     # the packer's bank-conflict model improves on the unarranged order and is >= the ideal
-    assert all(b["pred"][i] >= b["pred"][3 + i] for i in range(3))
+    assert all(b["pred"][i] >= b["pred"][5 + i] for i in range(3))
     os.environ["CHAIN_B200_PACK_EFFORT"] = "0"
     try:
         engine._prepared_cache.clear()
@@ -223,6 +228,95 @@ def test_den_packer_is_lossless(variant, S, K, D):
         os.environ.pop("CHAIN_B200_PACK_EFFORT")
         engine._prepared_cache.clear()
     assert sum(b["pred"][:3]) < sum(base["pred"][:3])
+
+
+def _blob_forward_backward(b, x, coeff):
+    """The factorised recursion of den_shared_kernel, run in float64 on the DECODED views of a blob for one
+    utterance (x = exp of the clamped nnet output, [T,D]): class sums through view 3, one arc per class in views 0
+    and 2, the one-operand beta' arcs of view 4 added to the rows of view 1 that carry the extra flag."""
+    S, D, S_pad, C = b["S"], b["D"], b["S_pad"], b["C"]
+    T = x.shape[0]
+    lk, ini, fin = (b[k].astype(np.float64) for k in ("leaky", "init", "final"))
+    v = [_decode_view(b["views"][i], b["nw"]) for i in range(5)]
+    flagged = set()
+    for code in list(b["views"][1]["rows"]) + [r for r, _, _ in b["views"][1]["split"]]:
+        if code >= 0 and code & 0x40000000:
+            flagged.add(code & 0xfffff)
+    assert flagged == {r for r, _, _, _ in v[4]}
+    R = b["R_pad"]
+
+    def two(view, A, Bv, n_rows):
+        out = np.zeros(n_rows)
+        for row, a_, b_, w in view:
+            out[row] += w * A[a_] * Bv[b_]
+        return out
+
+    def one(view, A, n_rows):
+        out = np.zeros(n_rows)
+        for row, a_, _, w in view:
+            out[row] += w * A[a_]
+        return out
+
+    alpha = np.zeros((T + 1, R))
+    tot = np.zeros(T + 1)
+    alpha[0, :S] = ini
+    tot[0] = ini.sum()
+    alpha[0, :S] += coeff * tot[0] * lk
+    for t in range(1, T + 1):
+        xs = x[t - 1] / tot[t - 1]
+        alpha[t - 1, S_pad:S_pad + max(C, 1)][:C] = one(v[3], alpha[t - 1], max(C, 1))[:C]
+        a = two(v[0], alpha[t - 1], xs, S)
+        tot[t] = a.sum()
+        alpha[t, :S] = a + coeff * tot[t] * lk
+    Z = (alpha[T, :S] * fin).sum()
+    logp = np.log(tot[:T]).sum() + np.log(Z)
+    beta = np.zeros(R)
+    beta[:S] = fin / Z + coeff * (fin * lk).sum() / Z
+    grad = np.zeros((T, D))
+    for t in range(T - 1, -1, -1):
+        xs = x[t] / tot[t]
+        for c in range(C):
+            beta[S_pad + c] = beta[b["cls_dst"][c]] * xs[b["cls_pdf"][c]]
+        grad[t] = two(v[2], alpha[t], beta, D) * xs
+        bp = two(v[1], beta, xs, S)
+        extra = one(v[4], beta, S)
+        for r in flagged:
+            bp[r] += extra[r]
+        beta[:S] = bp + coeff * (bp * lk).sum()
+    return logp, grad
+
+
+@pytest.mark.parametrize("variant,S,K,D,min_class", [("biphone", 150, 1400, 40, 4), ("biphone", 150, 1400, 40, 2),
+                                                     ("uniform", 60, 900, 3, 2), ("skew", 80, 1500, 2, 3)])
+def test_den_packer_class_factorisation(variant, S, K, D, min_class):
+    """(dst,pdf) classes: the packed views + class table reproduce the oracle's forward-backward exactly (up to
+    float64 reordering) -- structured graphs (pdf a function of the destination), graphs where only some arcs
+    share a class (few pdfs), and heavy rows split into sub-rows."""
+    from oracle import chain_oracle as co
+    g = ChainGraph(synth.random_den_fst(S, K, D, seed=19, variant=variant))
+    gb = ChainGraphBatch(g, 1)
+    gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_PROB)
+    os.environ["CHAIN_B200_MIN_CLASS"] = str(min_class)
+    try:
+        engine._prepared_cache.clear()
+        b = _parse_blob(engine.prepare_den_graph(gt, g.num_states, D, "cpu").blob_host)
+    finally:
+        os.environ.pop("CHAIN_B200_MIN_CLASS")
+        engine._prepared_cache.clear()
+    assert b["version"] == 10 and b["C"] > 0 and b["R_pad"] == b["S_pad"] + b["C_pad"]
+    # every arc is either a two-operand record of views 0/1/2 or a member of exactly one class (views 3 and 4)
+    n_cls_arcs = len(_decode_view(b["views"][3], 16))
+    assert n_cls_arcs == len(_decode_view(b["views"][4], 16)) >= min_class * b["C"]
+    assert len(_decode_view(b["views"][1], 16)) + n_cls_arcs == g.num_transitions
+    assert len(_decode_view(b["views"][0], 16)) == g.num_transitions - n_cls_arcs + b["C"]
+    assert len(_decode_view(b["views"][2], 16)) == g.num_transitions - n_cls_arcs + b["C"]
+    T = 9
+    x, lengths = synth.make_inputs(1, T, D, seed=20)
+    ex = x.clamp(-30, 30).exp()
+    o_c, lp_c, g_c, _, _ = co.den_c(gb, ex, lengths, 1e-5)
+    logp, grad = _blob_forward_backward(b, ex[0].double().numpy(), 1e-5)
+    assert abs(logp - o_c) < 2e-6 * abs(o_c) + 5e-6   # the oracle is fp32
+    assert np.abs(grad - g_c[0].numpy()).max() < 5e-6
 
 
 def test_den_packer_rejects_bad_graphs():

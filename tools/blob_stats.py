@@ -2,6 +2,7 @@
 import os, sys, struct, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pychain_b200 import synth, engine, ChainGraphBatch
+NAMES = ["alpha", "beta'", "gamma", "class", "beta'(cls)"]
 def stats(cfg, variant="uniform", B=None):
     c = synth.CONFIGS[cfg]
     g = synth.den_graph_for(cfg, variant=variant)
@@ -10,13 +11,20 @@ def stats(cfg, variant="uniform", B=None):
     engine._prepared_cache.clear()
     t = time.time(); prep = engine.prepare_den_graph(gt, g.num_states, c["D"], "cpu", batch_size=B or c["B"]); dt = time.time() - t
     h = prep.blob_host.numpy()
+    hdr = struct.unpack_from("<II12i", h, 0)
+    opt_g, C, C_pad, R_pad, max_sub = hdr[10], hdr[11], hdr[12], hdr[13], hdr[8]
     off = 56; out = []
-    opt_g = struct.unpack_from('<i', h, 40)[0]
-    for i in range(3):
+    for i in range(5):
         v = struct.unpack_from("<4i5q", h, off); off += 56; out.append(v)
-    tail = struct.unpack_from("<4q6d", h, off)
-    print(f"{cfg} {variant} G={opt_g}: pack {dt:.2f}s; " + "; ".join(
-        f"view{i}: slices {out[i][1]} split {out[i][2]} recs {out[i][4]} wf {tail[4+i]:.0f}/{tail[7+i]:.0f}={tail[4+i]/tail[7+i]:.3f}" for i in range(3)))
+    tail = struct.unpack_from("<6q10d", h, off)
+    print(f"{cfg} {variant} G={opt_g}: pack {dt:.2f}s; classes C={C} (R_pad={R_pad}), max_sub={max_sub}, blob {tail[5]/1e6:.2f} MB")
+    tot_wf = 0
+    for i in range(5):
+        wf, ideal = tail[6 + i], tail[11 + i]
+        tot_wf += wf
+        print(f"   view{i} {NAMES[i]:11s}: rows {out[i][0]} slices {out[i][1]} split {out[i][2]} recs {out[i][4]} "
+              f"wavefronts {wf:.0f} (ideal {ideal:.0f}" + (f", x{wf/ideal:.3f})" if ideal else ")"))
+    print(f"   modelled gather wavefronts per frame pair (class view counted once: its sums are spilled): {tot_wf:.0f}")
 if __name__ == "__main__":
     for a in (sys.argv[1:] or ["cfg4"]):
         cfg, _, var = a.partition(":")
