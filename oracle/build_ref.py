@@ -48,6 +48,7 @@ def is_built():
 def build(force=False, verbose=False):
     """Compile the reference extension.  Returns path of the .so, or None when
     the reference tree is absent (GPU box) and no prebuilt .so exists."""
+    stage_reference_loss()
     if is_built() and not force:
         if not have_reference():
             return OUT_SO
@@ -90,6 +91,21 @@ def build(force=False, verbose=False):
         print(" ".join(link))
     subprocess.check_call(link)
     return OUT_SO
+
+
+REF_LOSS = os.environ.get("PYCHAIN_REFERENCE", "/root/reference") + "/pychain/loss.py"
+STAGED_LOSS = os.path.join(OUT_DIR, "reference_pychain_loss.py")
+
+
+def stage_reference_loss():
+    """Stage the reference's UNMODIFIED pychain/loss.py next to the reference .so (oracle/_ref/ is git-ignored and
+    travels to the GPU box, where /root/reference does not exist).  tests/test_gpu_dropin.py runs that file, as is,
+    on top of the drop-in modules.  Never committed; returns the staged path or None."""
+    import shutil
+    if os.path.isfile(REF_LOSS):
+        os.makedirs(OUT_DIR, exist_ok=True)
+        shutil.copyfile(REF_LOSS, STAGED_LOSS)
+    return STAGED_LOSS if os.path.isfile(STAGED_LOSS) else None
 
 
 def load():
