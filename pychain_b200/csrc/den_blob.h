@@ -43,7 +43,7 @@
 namespace chainb200 {
 
 constexpr uint32_t kBlobMagic = 0x42324348u;  // "HC2B"
-constexpr uint32_t kBlobVersion = 10;
+constexpr uint32_t kBlobVersion = 11;
 #ifndef CHAIN_B200_NW
 #define CHAIN_B200_NW 16
 #endif

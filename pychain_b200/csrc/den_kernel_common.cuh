@@ -58,11 +58,12 @@ template <> __device__ __forceinline__ void st_vec<2>(float *p, const float (&v)
 }
 template <> __device__ __forceinline__ void st_vec<1>(float *p, const float (&v)[1]) { *p = v[0]; }
 
+// one lane's PAIR of records (16 bytes); a warp reads 512 contiguous bytes
 template <bool L1C>
-__device__ __forceinline__ uint2 ldg_stream(const uint2 *p) {
-  uint2 r;
-  if (L1C) asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-  else asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+  uint4 r;
+  if (L1C) asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  else asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
 

@@ -388,17 +388,25 @@ static void build_view(int n_rows, const ArcSet &arcs, int n_a, int n_b, bool st
     v.warp_info[3 * wv + 2] = (int64_t)rows_seq.size();
     for (int s : per[wv]) {
       rows_seq.insert(rows_seq.end(), v.rows.begin() + (size_t)s * 32, v.rows.begin() + (size_t)s * 32 + 32);
-      v.rec_ab.insert(v.rec_ab.end(), s_ab[s].begin(), s_ab[s].end());
-      v.rec_w.insert(v.rec_w.end(), s_w[s].begin(), s_w[s].end());
-      // end-of-slice flag on the last record of every lane: sign bit of the weight (probabilities
-      // are >= 0), or bit 31 of the index word for log-domain blobs
-      const size_t last = v.rec_w.size() - 32;
+      // records are consumed in pairs: the two records of a lane's pair are ADJACENT (16 bytes, one 128-bit
+      // load per lane and pair, 512 contiguous bytes per warp): [pair][lane][2]
+      const int width = v.width[s];
+      for (int j = 0; j < width / 2; j++)
+        for (int l = 0; l < 32; l++)
+          for (int h = 0; h < 2; h++) {
+            v.rec_ab.push_back(s_ab[s][(size_t)(2 * j + h) * 32 + l]);
+            v.rec_w.push_back(s_w[s][(size_t)(2 * j + h) * 32 + l]);
+          }
+      // end-of-slice flag on the second record of every lane's last pair: sign bit of the weight
+      // (probabilities are >= 0), or bit 31 of the index word for log-domain blobs
+      const size_t last = v.rec_w.size() - 64;
       for (int l = 0; l < 32; l++) {
+        const size_t q = last + 2 * l + 1;
         if (log_domain) {
-          v.rec_ab[last + l] |= 0x80000000u;
+          v.rec_ab[q] |= 0x80000000u;
         } else {
-          v.rec_w[last + l] = -fabsf(v.rec_w[last + l]);
-          if (!std::signbit(v.rec_w[last + l])) v.rec_w[last + l] = -0.0f;
+          v.rec_w[q] = -fabsf(v.rec_w[q]);
+          if (!std::signbit(v.rec_w[q])) v.rec_w[q] = -0.0f;
         }
       }
     }
@@ -532,11 +540,13 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
   }
   for (int c = 0; c < C; c++) a2.push(cls[c].pdf, (uint32_t)(S_pad + c) | ((uint32_t)cls[c].dst << 16), one);
   for (int i = 0; i < kNumViews; i++) vb[i] = ViewBuild();
-  build_view(S, a0, R_pad, D, so, log_domain, P, false, nullptr, Kv, false, vb[0]);
+  // n_a / n_b bound what an IDLE lane may gather (weight 0): only entries that always hold finite data, i.e. the
+  // S real states / D real pdfs -- never the row padding or the class extension (0 * garbage = NaN)
+  build_view(S, a0, S, D, so, log_domain, P, false, nullptr, Kv, false, vb[0]);
   build_view(S, a1, S, D, so, log_domain, P, false, C > 0 ? &flags1 : nullptr, Kv, false, vb[1]);
-  build_view(D, a2, R_pad, S, so, log_domain, P, false, nullptr, Kv, false, vb[2]);
+  build_view(D, a2, S, S, so, log_domain, P, false, nullptr, Kv, false, vb[2]);
   build_view(std::max(C, 1), a3, S, 1, so, log_domain, P, true, nullptr, Kv, true, vb[3]);
-  build_view(S, a4, R_pad, 1, so, log_domain, P, true, nullptr, Kv, true, vb[4]);
+  build_view(S, a4, S, 1, so, log_domain, P, true, nullptr, Kv, true, vb[4]);
   // split-row slots share the chip with the class sums: give classes back until everything fits
   int max_sub = 0;
   for (int i = 0; i < kNumViews; i++) max_sub = std::max(max_sub, vb[i].n_sub);

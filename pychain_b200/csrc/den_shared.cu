@@ -85,16 +85,13 @@ __device__ __forceinline__ void consume_rec1(const uint32_t ab, const float w, c
 template <int G, bool L1C, bool ONE, int NF, class Epi>
 __device__ __forceinline__ void sell_pass(const DView &v, const float *__restrict__ A, const float *__restrict__ Bv,
                                           float *__restrict__ partial, int warp, int lane, Epi &epi) {
-  const uint2 *sp = v.recs + v.warp_info[3 * warp] + lane;
+  const uint4 *sp = reinterpret_cast<const uint4 *>(v.recs + v.warp_info[3 * warp]) + lane;  // [pair][lane]: 2 records
   const int npairs = (int)v.warp_info[3 * warp + 1];
   const int32_t *rp = v.rows + v.warp_info[3 * warp + 2] + lane;
-  uint2 fa[NF][2], fb[NF][2];
+  uint4 fa[NF], fb[NF];
 #pragma unroll
-  for (int d = 0; d < NF; d++) {
-    fa[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
-    fa[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
-  }
-  sp += 2 * NF * 32;
+  for (int d = 0; d < NF; d++) fa[d] = ldg_stream<L1C>(sp + d * 32);
+  sp += NF * 32;
   int row = __ldg(rp), row_n1 = __ldg(rp + 32), row_n2 = __ldg(rp + 64);
   rp += 96;
   float acc[G];
@@ -122,38 +119,29 @@ __device__ __forceinline__ void sell_pass(const DView &v, const float *__restric
   int j = 0;
   for (; j + 2 * NF <= npairs; j += 2 * NF) {  // full double banks: straight-line code
 #pragma unroll
-    for (int d = 0; d < NF; d++) {
-      fb[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
-      fb[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
-    }
-    sp += 2 * NF * 32;
+    for (int d = 0; d < NF; d++) fb[d] = ldg_stream<L1C>(sp + d * 32);
+    sp += NF * 32;
 #pragma unroll
-    for (int d = 0; d < NF; d++) process(fa[d][0], fa[d][1]);
+    for (int d = 0; d < NF; d++) process(make_uint2(fa[d].x, fa[d].y), make_uint2(fa[d].z, fa[d].w));
 #pragma unroll
-    for (int d = 0; d < NF; d++) {
-      fa[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
-      fa[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
-    }
-    sp += 2 * NF * 32;
+    for (int d = 0; d < NF; d++) fa[d] = ldg_stream<L1C>(sp + d * 32);
+    sp += NF * 32;
 #pragma unroll
-    for (int d = 0; d < NF; d++) process(fb[d][0], fb[d][1]);
+    for (int d = 0; d < NF; d++) process(make_uint2(fb[d].x, fb[d].y), make_uint2(fb[d].z, fb[d].w));
   }
   const int rem = npairs - j;  // < 2*NF pairs left: bank A holds the first NF of them
   if (rem > 0) {
     if (rem > NF) {
 #pragma unroll
-      for (int d = 0; d < NF; d++) {
-        fb[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
-        fb[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
-      }
+      for (int d = 0; d < NF; d++) fb[d] = ldg_stream<L1C>(sp + d * 32);
     }
 #pragma unroll
     for (int d = 0; d < NF; d++)
-      if (d < rem) process(fa[d][0], fa[d][1]);
+      if (d < rem) process(make_uint2(fa[d].x, fa[d].y), make_uint2(fa[d].z, fa[d].w));
     if (rem > NF) {
 #pragma unroll
       for (int d = 0; d < NF; d++)
-        if (NF + d < rem) process(fb[d][0], fb[d][1]);
+        if (NF + d < rem) process(make_uint2(fb[d].x, fb[d].y), make_uint2(fb[d].z, fb[d].w));
     }
   }
 }

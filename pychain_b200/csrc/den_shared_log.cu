@@ -42,16 +42,13 @@ template <int G, bool L1C, class Epi>
 __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__restrict__ A,
                                               const float *__restrict__ Bv, float *__restrict__ partial, int warp,
                                               int lane, Epi &epi) {
-  const uint2 *sp = v.recs + v.warp_info[3 * warp] + lane;
+  const uint4 *sp = reinterpret_cast<const uint4 *>(v.recs + v.warp_info[3 * warp]) + lane;  // [pair][lane]: 2 records
   const int npairs = (int)v.warp_info[3 * warp + 1];
   const int32_t *rp = v.rows + v.warp_info[3 * warp + 2] + lane;
-  uint2 fa[kFifoPairs][2], fb[kFifoPairs][2];
+  uint4 fa[kFifoPairs], fb[kFifoPairs];
 #pragma unroll
-  for (int d = 0; d < kFifoPairs; d++) {
-    fa[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
-    fa[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
-  }
-  sp += 2 * kFifoPairs * 32;
+  for (int d = 0; d < kFifoPairs; d++) fa[d] = ldg_stream<L1C>(sp + d * 32);
+  sp += kFifoPairs * 32;
   int row = __ldg(rp), row_n1 = __ldg(rp + 32), row_n2 = __ldg(rp + 64);
   rp += 96;
   float m[G], s[G];
@@ -81,38 +78,29 @@ __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__res
   int j = 0;
   for (; j + 2 * kFifoPairs <= npairs; j += 2 * kFifoPairs) {
 #pragma unroll
-    for (int d = 0; d < kFifoPairs; d++) {
-      fb[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
-      fb[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
-    }
-    sp += 2 * kFifoPairs * 32;
+    for (int d = 0; d < kFifoPairs; d++) fb[d] = ldg_stream<L1C>(sp + d * 32);
+    sp += kFifoPairs * 32;
 #pragma unroll
-    for (int d = 0; d < kFifoPairs; d++) process(fa[d][0], fa[d][1]);
+    for (int d = 0; d < kFifoPairs; d++) process(make_uint2(fa[d].x, fa[d].y), make_uint2(fa[d].z, fa[d].w));
 #pragma unroll
-    for (int d = 0; d < kFifoPairs; d++) {
-      fa[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
-      fa[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
-    }
-    sp += 2 * kFifoPairs * 32;
+    for (int d = 0; d < kFifoPairs; d++) fa[d] = ldg_stream<L1C>(sp + d * 32);
+    sp += kFifoPairs * 32;
 #pragma unroll
-    for (int d = 0; d < kFifoPairs; d++) process(fb[d][0], fb[d][1]);
+    for (int d = 0; d < kFifoPairs; d++) process(make_uint2(fb[d].x, fb[d].y), make_uint2(fb[d].z, fb[d].w));
   }
   const int rem = npairs - j;
   if (rem > 0) {
     if (rem > kFifoPairs) {
 #pragma unroll
-      for (int d = 0; d < kFifoPairs; d++) {
-        fb[d][0] = ldg_stream<L1C>(sp + (2 * d) * 32);
-        fb[d][1] = ldg_stream<L1C>(sp + (2 * d + 1) * 32);
-      }
+      for (int d = 0; d < kFifoPairs; d++) fb[d] = ldg_stream<L1C>(sp + d * 32);
     }
 #pragma unroll
     for (int d = 0; d < kFifoPairs; d++)
-      if (d < rem) process(fa[d][0], fa[d][1]);
+      if (d < rem) process(make_uint2(fa[d].x, fa[d].y), make_uint2(fa[d].z, fa[d].w));
     if (rem > kFifoPairs) {
 #pragma unroll
       for (int d = 0; d < kFifoPairs; d++)
-        if (kFifoPairs + d < rem) process(fb[d][0], fb[d][1]);
+        if (kFifoPairs + d < rem) process(make_uint2(fb[d].x, fb[d].y), make_uint2(fb[d].z, fb[d].w));
     }
   }
 }

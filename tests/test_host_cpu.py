@@ -169,7 +169,7 @@ def _decode_view(v, nw):
         pending = [[] for _ in range(32)]
         for j in range(npairs):
             for half in range(2):
-                blk = v["recs"][rec0 + (2 * j + half) * 32: rec0 + (2 * j + half) * 32 + 32]
+                blk = v["recs"][rec0 + j * 64 + half: rec0 + (j + 1) * 64: 2]   # [pair][lane][2 records]
                 for lane in range(32):
                     ab, wb = int(blk[lane, 0]), int(blk[lane, 1])
                     wt = np.frombuffer(np.uint32(wb & 0x7fffffff).tobytes(), np.float32)[0]
@@ -303,7 +303,7 @@ def test_den_packer_class_factorisation(variant, S, K, D, min_class):
     finally:
         os.environ.pop("CHAIN_B200_MIN_CLASS")
         engine._prepared_cache.clear()
-    assert b["version"] == 10 and b["C"] > 0 and b["R_pad"] == b["S_pad"] + b["C_pad"]
+    assert b["version"] == 11 and b["C"] > 0 and b["R_pad"] == b["S_pad"] + b["C_pad"]
     # every arc is either a two-operand record of views 0/1/2 or a member of exactly one class (views 3 and 4)
     n_cls_arcs = len(_decode_view(b["views"][3], 16))
     assert n_cls_arcs == len(_decode_view(b["views"][4], 16)) >= min_class * b["C"]
