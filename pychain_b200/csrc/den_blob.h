@@ -43,7 +43,8 @@
 namespace chainb200 {
 
 constexpr uint32_t kBlobMagic = 0x42324348u;  // "HC2B"
-constexpr uint32_t kBlobVersion = 11;
+constexpr uint32_t kBlobVersion = 12;
+constexpr uint32_t kCodeMarkLog = 0x7fc0c0deu;  // log-domain blobs: weight word of a row-code slot (a NaN no arc can carry)
 #ifndef CHAIN_B200_NW
 #define CHAIN_B200_NW 16
 #endif

@@ -239,7 +239,7 @@ struct ArcSet {
 // row_flags: optional per-row bits OR-ed into the row code (kRowExtraFlag).
 static void build_view(int n_rows, const ArcSet &arcs, int n_a, int n_b, bool structure_only, bool log_domain, int P,
                        bool skip_empty, const std::vector<int32_t> *row_flags, int effort_K, bool one_operand,
-                       ViewBuild &v) {
+                       const float *row_aux, ViewBuild &v) {
   v.n_rows = n_rows;
   const int K = arcs.size();
   const std::vector<int32_t> &row_of = arcs.row_of;
@@ -311,14 +311,32 @@ static void build_view(int n_rows, const ArcSet &arcs, int n_a, int n_b, bool st
       v.rows[i] = lanes[l]->row_code;
       width = std::max(width, (int)lanes[l]->arcs.size());
     }
-    width = std::max(2, width + (width & 1));  // pairs; an empty slice still runs its epilogue
+    // the LAST slot of every lane is not an arc: it carries the lane's row code (and one float the epilogue wants,
+    // e.g. leaky(row) for the beta' pass) through the same prefetched stream as the records, so the end of a
+    // slice costs no load of its own -- slices of one or two arcs (chain graphs are full of them) would otherwise
+    // expose a full L2 latency each.  Slots are consumed in pairs: width = arcs + 1, rounded up to even.
+    width = (width + 2) & ~1;
     std::vector<int> cols;
-    arrange_slice(lanes, width, cols, rng, structure_only ? 0 : effort, P);
-    width = (int)(cols.size() / 32);
+    arrange_slice(lanes, width - 1, cols, rng, structure_only ? 0 : effort, P);
     v.width[s] = width;
     s_ab[s].assign((size_t)width * 32, 0u);
     s_w[s].assign((size_t)width * 32, log_domain ? -INFINITY : 0.f);
-    for (int k = 0; k < width; k++) {
+    for (int l = 0; l < 32; l++) {
+      const size_t i = (size_t)s * 32 + l;
+      const int32_t code = (i < units.size()) ? lanes[l]->row_code : -1;
+      float aux = (row_aux && code >= 0) ? fabsf(row_aux[code & 0xfffff]) : 0.f;
+      uint32_t mark;
+      if (log_domain) {
+        mark = kCodeMarkLog;
+      } else {
+        aux = -aux;                                   // sign bit = "this slot is the row code" (arc weights are >= 0)
+        if (!std::signbit(aux)) aux = -0.0f;
+        memcpy(&mark, &aux, 4);
+      }
+      s_ab[s][(size_t)(width - 1) * 32 + l] = (uint32_t)code;
+      memcpy(&s_w[s][(size_t)(width - 1) * 32 + l], &mark, 4);
+    }
+    for (int k = 0; k < width - 1; k++) {
       uint32_t ia[32], ib[32];
       for (int l = 0; l < 32; l++) {
         const int j = cols[(size_t)k * 32 + l];
@@ -380,14 +398,11 @@ static void build_view(int n_rows, const ArcSet &arcs, int n_a, int n_b, bool st
   v.warp_info.assign((size_t)DEN_NW * 3, 0);
   v.rec_ab.clear();
   v.rec_w.clear();
-  std::vector<int32_t> rows_seq;
-  rows_seq.reserve(((size_t)n_slices + 3 * DEN_NW) * 32);
   for (int wv = 0; wv < DEN_NW; wv++) {
     const size_t rec0 = v.rec_ab.size();
     v.warp_info[3 * wv + 0] = (int64_t)rec0;
-    v.warp_info[3 * wv + 2] = (int64_t)rows_seq.size();
+    v.warp_info[3 * wv + 2] = (int64_t)per[wv].size();   // slices of this warp (informational)
     for (int s : per[wv]) {
-      rows_seq.insert(rows_seq.end(), v.rows.begin() + (size_t)s * 32, v.rows.begin() + (size_t)s * 32 + 32);
       // records are consumed in pairs: the two records of a lane's pair are ADJACENT (16 bytes, one 128-bit
       // load per lane and pair, 512 contiguous bytes per warp): [pair][lane][2]
       const int width = v.width[s];
@@ -397,27 +412,14 @@ static void build_view(int n_rows, const ArcSet &arcs, int n_a, int n_b, bool st
             v.rec_ab.push_back(s_ab[s][(size_t)(2 * j + h) * 32 + l]);
             v.rec_w.push_back(s_w[s][(size_t)(2 * j + h) * 32 + l]);
           }
-      // end-of-slice flag on the second record of every lane's last pair: sign bit of the weight
-      // (probabilities are >= 0), or bit 31 of the index word for log-domain blobs
-      const size_t last = v.rec_w.size() - 64;
-      for (int l = 0; l < 32; l++) {
-        const size_t q = last + 2 * l + 1;
-        if (log_domain) {
-          v.rec_ab[q] |= 0x80000000u;
-        } else {
-          v.rec_w[q] = -fabsf(v.rec_w[q]);
-          if (!std::signbit(v.rec_w[q])) v.rec_w[q] = -0.0f;
-        }
-      }
     }
-    rows_seq.insert(rows_seq.end(), 3 * 32, -1);  // the row prefetch runs slices ahead
     size_t pairs = (v.rec_ab.size() - rec0) / 64;
     const size_t run = pairs;  // the kernel runs the last (partial) double bank through a predicated tail
     v.warp_info[3 * wv + 1] = (int64_t)run;
     v.rec_ab.insert(v.rec_ab.end(), (size_t)3 * kFifoPairs * 64, 0u);  // register-bank run-out
     v.rec_w.insert(v.rec_w.end(), (size_t)3 * kFifoPairs * 64, log_domain ? -INFINITY : 0.f);
   }
-  v.rows.swap(rows_seq);
+  v.rows.clear();   // the row codes travel inside the record streams
 }
 
 }  // namespace
@@ -542,11 +544,11 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
   for (int i = 0; i < kNumViews; i++) vb[i] = ViewBuild();
   // n_a / n_b bound what an IDLE lane may gather (weight 0): only entries that always hold finite data, i.e. the
   // S real states / D real pdfs -- never the row padding or the class extension (0 * garbage = NaN)
-  build_view(S, a0, S, D, so, log_domain, P, false, nullptr, Kv, false, vb[0]);
-  build_view(S, a1, S, D, so, log_domain, P, false, C > 0 ? &flags1 : nullptr, Kv, false, vb[1]);
-  build_view(D, a2, S, S, so, log_domain, P, false, nullptr, Kv, false, vb[2]);
-  build_view(std::max(C, 1), a3, S, 1, so, log_domain, P, true, nullptr, Kv, true, vb[3]);
-  build_view(S, a4, S, 1, so, log_domain, P, true, nullptr, Kv, true, vb[4]);
+  build_view(S, a0, S, D, so, log_domain, P, false, nullptr, Kv, false, nullptr, vb[0]);
+  build_view(S, a1, S, D, so, log_domain, P, false, C > 0 ? &flags1 : nullptr, Kv, false, log_domain ? nullptr : leaky, vb[1]);
+  build_view(D, a2, S, S, so, log_domain, P, false, nullptr, Kv, false, nullptr, vb[2]);
+  build_view(std::max(C, 1), a3, S, 1, so, log_domain, P, true, nullptr, Kv, true, nullptr, vb[3]);
+  build_view(S, a4, S, 1, so, log_domain, P, true, nullptr, Kv, true, nullptr, vb[4]);
   // split-row slots share the chip with the class sums: give classes back until everything fits
   int max_sub = 0;
   for (int i = 0; i < kNumViews; i++) max_sub = std::max(max_sub, vb[i].n_sub);

@@ -62,6 +62,13 @@ __device__ __forceinline__ void consume_rec(const uint32_t ab, const float w, co
 #define CHAIN_B200_NF2_G4 (kFifoPairs - 1)
 #endif
 template <int G> __host__ __device__ constexpr int nf2() { return G == 4 ? CHAIN_B200_NF2_G4 : kFifoPairs; }
+// One-operand passes (class views) have cheap pairs: a bank must cover the L2 latency with fewer cycles of work
+// per pair, and they hold 8 fewer operand registers, so their banks are deeper.  (The streams' run-out, 3 *
+// kFifoPairs pairs, covers banks of up to 3 * kFifoPairs pairs.)
+#ifndef CHAIN_B200_NF1_G4
+#define CHAIN_B200_NF1_G4 6
+#endif
+template <int G> __host__ __device__ constexpr int nf1() { return G == 4 ? CHAIN_B200_NF1_G4 : kFifoPairs; }
 
 // One-operand record (class views 3 and 4): acc += A[a] * w.
 template <int G>
@@ -85,35 +92,29 @@ __device__ __forceinline__ void consume_rec1(const uint32_t ab, const float w, c
 template <int G, bool L1C, bool ONE, int NF, class Epi>
 __device__ __forceinline__ void sell_pass(const DView &v, const float *__restrict__ A, const float *__restrict__ Bv,
                                           float *__restrict__ partial, int warp, int lane, Epi &epi) {
-  const uint4 *sp = reinterpret_cast<const uint4 *>(v.recs + v.warp_info[3 * warp]) + lane;  // [pair][lane]: 2 records
+  const uint4 *sp = reinterpret_cast<const uint4 *>(v.recs + v.warp_info[3 * warp]) + lane;  // [pair][lane]: 2 slots
   const int npairs = (int)v.warp_info[3 * warp + 1];
-  const int32_t *rp = v.rows + v.warp_info[3 * warp + 2] + lane;
   uint4 fa[NF], fb[NF];
 #pragma unroll
   for (int d = 0; d < NF; d++) fa[d] = ldg_stream<L1C>(sp + d * 32);
   sp += NF * 32;
-  int row = __ldg(rp), row_n1 = __ldg(rp + 32), row_n2 = __ldg(rp + 64);
-  rp += 96;
   float acc[G];
 #pragma unroll
   for (int g = 0; g < G; g++) acc[g] = 0.f;
+  // A pair is two arcs, or -- at the end of a slice -- an arc and the lane's ROW-CODE slot (sign bit of its second
+  // word; warp-uniform): {row code, -aux}.  The code arrives through the same prefetched stream as the arcs.
   auto process = [&](const uint2 r0, const uint2 r1) {
-    if constexpr (ONE) {
-      consume_rec1<G>(r0.x, __uint_as_float(r0.y), A, acc);
-      consume_rec1<G>(r1.x, __uint_as_float(r1.y & 0x7fffffffu), A, acc);
-    } else {
-      consume_rec<G>(r0.x, __uint_as_float(r0.y), A, Bv, acc);
-      consume_rec<G>(r1.x, __uint_as_float(r1.y & 0x7fffffffu), A, Bv, acc);
-    }
-    if (r1.y & 0x80000000u) {  // warp-uniform: last pair of the slice
-      if (row >= 0) epi(row, acc);
+    if constexpr (ONE) consume_rec1<G>(r0.x, __uint_as_float(r0.y), A, acc);
+    else consume_rec<G>(r0.x, __uint_as_float(r0.y), A, Bv, acc);
+    if (r1.y & 0x80000000u) {
+      const int row = (int)r1.x;
+      if (row >= 0) epi(row, acc, __uint_as_float(r1.y & 0x7fffffffu));
       else if (row <= -2) st_vec<G>(partial + (size_t)(-2 - row) * G, acc);
 #pragma unroll
       for (int g = 0; g < G; g++) acc[g] = 0.f;
-      row = row_n1;
-      row_n1 = row_n2;
-      row_n2 = __ldg(rp);
-      rp += 32;
+    } else {
+      if constexpr (ONE) consume_rec1<G>(r1.x, __uint_as_float(r1.y), A, acc);
+      else consume_rec<G>(r1.x, __uint_as_float(r1.y), A, Bv, acc);
     }
   };
   int j = 0;
@@ -146,9 +147,11 @@ __device__ __forceinline__ void sell_pass(const DView &v, const float *__restric
   }
 }
 
-// Rows that were split: add the sub-row partial sums (fixed order) and run the epilogue.
+// Rows that were split: add the sub-row partial sums (fixed order) and run the epilogue.  `aux_tab`: the per-row
+// float the row-code slot would have carried (leaky probabilities for the beta' pass), or null.
 template <int G, class Epi>
-__device__ __forceinline__ void fixup_split(const DView &v, const float *__restrict__ partial, Epi &epi) {
+__device__ __forceinline__ void fixup_split(const DView &v, const float *__restrict__ partial,
+                                            const float *__restrict__ aux_tab, Epi &epi) {
   for (int i = threadIdx.x; i < v.n_split; i += DEN_NT) {
     const int row = v.split[3 * i], first = v.split[3 * i + 1], cnt = v.split[3 * i + 2];
     float acc[G];
@@ -160,7 +163,7 @@ __device__ __forceinline__ void fixup_split(const DView &v, const float *__restr
 #pragma unroll
       for (int g = 0; g < G; g++) acc[g] += t[g];
     }
-    epi(row, acc);
+    epi(row, acc, aux_tab ? __ldg(aux_tab + (row & (kRowExtraFlag - 1))) : 0.f);
   }
 }
 
@@ -314,25 +317,25 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         // class sums A_c(t-1) = sum_{arcs of class c} alpha'(t-1,src) * w: one operand per arc.  They extend the
         // state row (virtual states S_pad + c) and are spilled with it: the backward pass needs them again.
         float *aext = A + (size_t)S_pad * G, *wext = aws + ((size_t)(t - 1) * R_pad + S_pad) * G;
-        auto epi_cls = [&](int row, const float (&acc)[G]) {
+        auto epi_cls = [&](int row, const float (&acc)[G], float) {
           st_vec<G>(aext + (size_t)row * G, acc);
           st_vec<G>(wext + (size_t)row * G, acc);
         };
-        sell_pass<G, L1C, true, kFifoPairs>(views[3], A, nullptr, partial, warp, lane, epi_cls);
-        if (p.view[3].n_split) { __syncthreads(); fixup_split<G>(p.view[3], partial, epi_cls); }
+        sell_pass<G, L1C, true, nf1<G>()>(views[3], A, nullptr, partial, warp, lane, epi_cls);
+        if (p.view[3].n_split) { __syncthreads(); fixup_split<G>(p.view[3], partial, nullptr, epi_cls); }
       }
       __syncthreads();  // x_s complete, xraw free, class sums complete
       if (t < Lmax) issue_x(t);
       float part[G];
 #pragma unroll
       for (int g = 0; g < G; g++) part[g] = 0.f;
-      auto epi_fwd = [&](int row, const float (&acc)[G]) {
+      auto epi_fwd = [&](int row, const float (&acc)[G], float) {
 #pragma unroll
         for (int g = 0; g < G; g++) part[g] += acc[g];
         st_vec<G>(Bn + (size_t)row * G, acc);
       };
       sell_pass<G, L1C, false, nf2<G>()>(views[0], A, x_s, partial, warp, lane, epi_fwd);
-      if (p.view[0].n_split) { __syncthreads(); fixup_split<G>(p.view[0], partial, epi_fwd); }
+      if (p.view[0].n_split) { __syncthreads(); fixup_split<G>(p.view[0], partial, nullptr, epi_fwd); }
 #pragma unroll
       for (int g = 0; g < G; g++) {
         part[g] = warp_sum(part[g]);
@@ -436,7 +439,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       }
 
       // ---- gamma pass: rows = pdfs; gamma(t,n) = x(t,n)/tot(t) * sum alpha'(src) p beta(dst)
-      auto epi_gam = [&](int row, const float (&acc)[G]) {
+      auto epi_gam = [&](int row, const float (&acc)[G], float) {
         float xv[G], o[G];
         ld_vec<G>(x_s + (size_t)row * G, xv);
 #pragma unroll
@@ -444,14 +447,14 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         st_vec<G>(gam_s + (size_t)row * G, o);
       };
       sell_pass<G, L1C, false, nf2<G>()>(views[2], P, Q, partial, warp, lane, epi_gam);
-      if (p.view[2].n_split) { __syncthreads(); fixup_split<G>(p.view[2], partial, epi_gam); }
+      if (p.view[2].n_split) { __syncthreads(); fixup_split<G>(p.view[2], partial, nullptr, epi_gam); }
       __syncthreads();  // gamma rows complete; everybody done reading P; bx complete
 
       // ---- beta' pass, class arcs: rows = source states, one operand (bx_c) per arc; the raw sums wait in P
       if (C) {
-        auto epi_b2 = [&](int row, const float (&acc)[G]) { st_vec<G>(P + (size_t)row * G, acc); };
-        sell_pass<G, L1C, true, kFifoPairs>(views[4], Q, nullptr, partial, warp, lane, epi_b2);
-        if (p.view[4].n_split) { __syncthreads(); fixup_split<G>(p.view[4], partial, epi_b2); }
+        auto epi_b2 = [&](int row, const float (&acc)[G], float) { st_vec<G>(P + (size_t)row * G, acc); };
+        sell_pass<G, L1C, true, nf1<G>()>(views[4], Q, nullptr, partial, warp, lane, epi_b2);
+        if (p.view[4].n_split) { __syncthreads(); fixup_split<G>(p.view[4], partial, nullptr, epi_b2); }
         __syncthreads();
       }
 
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       float lpart[G];
 #pragma unroll
       for (int g = 0; g < G; g++) lpart[g] = 0.f;
-      auto epi_bwd = [&](int code, const float (&acc)[G]) {
+      auto epi_bwd = [&](int code, const float (&acc)[G], float l /* leaky(row), from the row-code slot */) {
         const int row = code & (kRowExtraFlag - 1);
         float o[G];
 #pragma unroll
@@ -470,13 +473,12 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
 #pragma unroll
           for (int g = 0; g < G; g++) o[g] += e[g];
         }
-        const float l = __ldg(lk + row);
 #pragma unroll
         for (int g = 0; g < G; g++) lpart[g] = fmaf(o[g], l, lpart[g]);
         st_vec<G>(P + (size_t)row * G, o);
       };
       sell_pass<G, L1C, false, nf2<G>()>(views[1], Q, x_s, partial, warp, lane, epi_bwd);
-      if (p.view[1].n_split) { __syncthreads(); fixup_split<G>(p.view[1], partial, epi_bwd); }
+      if (p.view[1].n_split) { __syncthreads(); fixup_split<G>(p.view[1], partial, lk, epi_bwd); }
 #pragma unroll
       for (int g = 0; g < G; g++) {
         lpart[g] = warp_sum(lpart[g]);

@@ -29,7 +29,7 @@ __device__ __forceinline__ void lse_rec(const uint32_t ab, const float w, const 
                                         const float *__restrict__ Bv, float (&m)[G], float (&s)[G]) {
   float a[G], b[G];
   ld_vec<G>(A + (ab & 0xffffu) * G, a);
-  ld_vec<G>(Bv + ((ab >> 16) & 0x7fffu) * G, b);
+  ld_vec<G>(Bv + (ab >> 16) * G, b);
 #pragma unroll
   for (int g = 0; g < G; g++) lse_add_fast(m[g], s[g], a[g] + w + b[g]);
 }
@@ -44,20 +44,18 @@ __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__res
                                               int lane, Epi &epi) {
   const uint4 *sp = reinterpret_cast<const uint4 *>(v.recs + v.warp_info[3 * warp]) + lane;  // [pair][lane]: 2 records
   const int npairs = (int)v.warp_info[3 * warp + 1];
-  const int32_t *rp = v.rows + v.warp_info[3 * warp + 2] + lane;
   uint4 fa[kFifoPairs], fb[kFifoPairs];
 #pragma unroll
   for (int d = 0; d < kFifoPairs; d++) fa[d] = ldg_stream<L1C>(sp + d * 32);
   sp += kFifoPairs * 32;
-  int row = __ldg(rp), row_n1 = __ldg(rp + 32), row_n2 = __ldg(rp + 64);
-  rp += 96;
   float m[G], s[G];
 #pragma unroll
   for (int g = 0; g < G; g++) { m[g] = -INFINITY; s[g] = 0.f; }
+  // a pair is two arcs, or -- at the end of a slice -- an arc and the lane's row-code slot (weight word = kCodeMarkLog)
   auto process = [&](const uint2 r0, const uint2 r1) {
     lse_rec<G>(r0.x, __uint_as_float(r0.y), A, Bv, m, s);
-    lse_rec<G>(r1.x, __uint_as_float(r1.y), A, Bv, m, s);
-    if (r1.x & 0x80000000u) {  // warp-uniform: last pair of the slice
+    if (r1.y == kCodeMarkLog) {  // warp-uniform: end of the slice
+      const int row = (int)r1.x;
       if (row >= 0) {
         float o[G];
 #pragma unroll
@@ -69,10 +67,8 @@ __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__res
       }
 #pragma unroll
       for (int g = 0; g < G; g++) { m[g] = -INFINITY; s[g] = 0.f; }
-      row = row_n1;
-      row_n1 = row_n2;
-      row_n2 = __ldg(rp);
-      rp += 32;
+    } else {
+      lse_rec<G>(r1.x, __uint_as_float(r1.y), A, Bv, m, s);
     }
   };
   int j = 0;

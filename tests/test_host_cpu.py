@@ -142,7 +142,7 @@ def _parse_blob(blob):
         n_rows, n_slices, n_split, n_sub, n_recs, o_info, o_rows, o_recs, o_split = struct.unpack_from("<4i5q", h, off)
         off += 56
         info = np.frombuffer(h, np.int64, nw * 3, o_info).reshape(nw, 3)
-        rows = np.frombuffer(h, np.int32, (n_slices + 3 * nw) * 32, o_rows)
+        rows = np.zeros(0, np.int32)   # row codes travel inside the record streams
         recs = np.frombuffer(h, np.uint32, n_recs * 2, o_recs).reshape(-1, 2)
         split = np.frombuffer(h, np.int32, n_split * 3, o_split).reshape(-1, 3)
         views.append(dict(n_rows=n_rows, n_slices=n_slices, n_sub=n_sub, info=info, rows=rows, recs=recs, split=split))
@@ -156,7 +156,9 @@ def _parse_blob(blob):
 
 
 def _decode_view(v, nw):
-    """Walk the per-warp streams exactly like sell_pass does: returns {(row, a, b, w_bits) multiset}."""
+    """Walk the per-warp streams exactly like sell_pass does: returns {(row, a, b, w) multiset}.  Slots come in
+    pairs, [pair][lane][2]; the second slot of a slice's last pair is the lane's row code (sign bit of its weight
+    word), everything else is an arc (weight 0 = idle)."""
     out = []
     sub_owner = {}
     for row, first, cnt in v["split"]:
@@ -164,31 +166,32 @@ def _decode_view(v, nw):
             sub_owner[first + j] = row
     slices_seen = 0
     for w in range(nw):
-        rec0, npairs, row0 = v["info"][w]
-        rp = row0
+        rec0, npairs, nsl = v["info"][w]
         pending = [[] for _ in range(32)]
+        seen_w = 0
         for j in range(npairs):
-            for half in range(2):
-                blk = v["recs"][rec0 + j * 64 + half: rec0 + (j + 1) * 64: 2]   # [pair][lane][2 records]
-                for lane in range(32):
-                    ab, wb = int(blk[lane, 0]), int(blk[lane, 1])
-                    wt = np.frombuffer(np.uint32(wb & 0x7fffffff).tobytes(), np.float32)[0]
+            blk = v["recs"][rec0 + j * 64: rec0 + (j + 1) * 64].reshape(32, 2, 2)   # [lane][slot][word]
+            flags = (blk[:, 1, 1] >> 31) & 1
+            assert flags.min() == flags.max(), "end-of-slice flag must be warp-uniform"
+            for lane in range(32):
+                for slot in range(2):
+                    if slot == 1 and flags[0]:
+                        continue
+                    ab, wb = int(blk[lane, slot, 0]), int(blk[lane, slot, 1])
+                    assert not (wb >> 31), "arc weights are >= 0"
+                    wt = np.frombuffer(np.uint32(wb).tobytes(), np.float32)[0]
                     if wt != 0.0:
                         pending[lane].append((ab & 0xffff, ab >> 16, wt))
-                if half == 1:
-                    flags = (blk[:, 1] >> 31) & 1
-                    assert flags.min() == flags.max(), "end-of-slice flag must be warp-uniform"
-                    if flags[0]:
-                        codes = v["rows"][rp: rp + 32]
-                        rp += 32
-                        slices_seen += 1
-                        for lane in range(32):
-                            code = int(codes[lane])
-                            row = (code & 0xfffff) if code >= 0 else ((sub_owner[-2 - code] & 0xfffff) if code <= -2 else None)
-                            assert row is not None or not pending[lane]
-                            out += [(row,) + t for t in pending[lane]]
-                            pending[lane] = []
-        assert not any(pending)
+            if flags[0]:
+                slices_seen += 1
+                seen_w += 1
+                for lane in range(32):
+                    code = int(np.int32(blk[lane, 1, 0]))
+                    row = (code & 0xfffff) if code >= 0 else ((sub_owner[-2 - code] & 0xfffff) if code <= -2 else None)
+                    assert row is not None or not pending[lane]
+                    out += [(row,) + t for t in pending[lane]]
+                    pending[lane] = []
+        assert not any(pending) and seen_w == nsl
     assert slices_seen == v["n_slices"]
     return sorted(out)
 
@@ -239,9 +242,16 @@ def _blob_forward_backward(b, x, coeff):
     lk, ini, fin = (b[k].astype(np.float64) for k in ("leaky", "init", "final"))
     v = [_decode_view(b["views"][i], b["nw"]) for i in range(5)]
     flagged = set()
-    for code in list(b["views"][1]["rows"]) + [r for r, _, _ in b["views"][1]["split"]]:
+    v1 = b["views"][1]
+    codes = [int(np.int32(c)) for c, wb in v1["recs"] if wb >> 31] + [int(r) for r, _, _ in v1["split"]]
+    for code in codes:
         if code >= 0 and code & 0x40000000:
             flagged.add(code & 0xfffff)
+    # the row-code slots of view 1 carry leaky(row)
+    for c, wb in v1["recs"]:
+        if wb >> 31 and np.int32(c) >= 0:
+            lv = np.frombuffer(np.uint32(wb & 0x7fffffff).tobytes(), np.float32)[0]
+            assert lv == b["leaky"][int(np.int32(c)) & 0xfffff]
     assert flagged == {r for r, _, _, _ in v[4]}
     R = b["R_pad"]
 
@@ -303,7 +313,7 @@ def test_den_packer_class_factorisation(variant, S, K, D, min_class):
     finally:
         os.environ.pop("CHAIN_B200_MIN_CLASS")
         engine._prepared_cache.clear()
-    assert b["version"] == 11 and b["C"] > 0 and b["R_pad"] == b["S_pad"] + b["C_pad"]
+    assert b["version"] == 12 and b["C"] > 0 and b["R_pad"] == b["S_pad"] + b["C_pad"]
     # every arc is either a two-operand record of views 0/1/2 or a member of exactly one class (views 3 and 4)
     n_cls_arcs = len(_decode_view(b["views"][3], 16))
     assert n_cls_arcs == len(_decode_view(b["views"][4], 16)) >= min_class * b["C"]
