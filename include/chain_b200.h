@@ -86,6 +86,9 @@ size_t chain_b200_workspace_bytes(int B, int T, int D, int S, int K, unsigned fl
  * logp_dev   f32 [B]      per-sequence log p (may be NULL)
  * grad_dev   f32 [B,T,D]  d objf / d log-prob = arc posteriors summed per pdf; rows t >= len are 0.
  *                         Every element is written (no pre-zeroing needed).
+ *                         The posteriors are multiplied by `grad_scale` as they are written: pass 1 for the
+ *                         reference's output; ChainLoss passes +-1/sum(lengths) (loss.py:85,102-104), so that
+ *                         d loss/d x leaves the kernel finished (ignored with CHAIN_B200_GRAD_AS_LOG).
  * ok_dev     i32 [1]      the reference's self-check verdict (chain-computation.cc:345-391), 1 = ok
  * diag_dev   f32 [8]      {sum_b sum_i alpha'(0,i) beta'(0,i), sum_b sum_n gamma(0,n), objf, valid frames
  *                         (sum_b min(len_b, T)), 1 - ok, 0, 0, 0} (may be NULL).  Elements 2..4 are the numbers a
@@ -96,7 +99,7 @@ int chain_b200_forward_backward(
     const int32_t *bwd_trans_dev, const int32_t *bwd_idx_dev, const float *bwd_probs_dev,
     const float *leaky_dev, const float *init_dev, const float *final_dev,
     const float *x_dev, const int64_t *lengths_dev,
-    int B, int T, int D, int S, int K, float leaky_coeff, unsigned flags,
+    int B, int T, int D, int S, int K, float leaky_coeff, unsigned flags, float grad_scale,
     float *objf_dev, float *logp_dev, float *grad_dev, int32_t *ok_dev, float *diag_dev,
     void *workspace_dev, size_t workspace_bytes, int device, void *stream);
 
@@ -108,7 +111,7 @@ int chain_b200_forward_backward_log_domain(
     const int32_t *bwd_trans_dev, const int32_t *bwd_idx_dev, const float *bwd_probs_dev,
     const float *init_dev, const float *final_dev,
     const float *x_dev, const int64_t *lengths_dev,
-    int B, int T, int D, int S, int K, unsigned flags,
+    int B, int T, int D, int S, int K, unsigned flags, float grad_scale,
     float *objf_dev, float *logp_dev, float *grad_dev, int32_t *ok_dev, float *diag_dev,
     void *workspace_dev, size_t workspace_bytes, int device, void *stream);
 
@@ -150,9 +153,20 @@ int chain_b200_den_group_width(int S, int D, int B, int device);
 int chain_b200_den_forward_backward(
     const void *blob_host, const void *blob_dev, int blob_copies,
     const float *x_dev, const int64_t *lengths_dev,
-    int B, int T, int D, float leaky_coeff, unsigned flags,
+    int B, int T, int D, float leaky_coeff, unsigned flags, float grad_scale,
     float *objf_dev, float *logp_dev, float *grad_dev, int32_t *ok_dev, float *diag_dev,
     void *workspace_dev, size_t workspace_bytes, int device, void *stream);
+
+/* ---- the rest of pychain/loss.py:97-105, fused ------------------------------
+ * chain_b200_combine_loss: grad_den[i] += grad_num[i] for i < n (both already scaled, see grad_scale) and
+ *   loss[0] = (objf_den[0] - objf_num[0]) * loss_scale, i.e. -(num - den) [/ sum(lengths)] (loss.py:102-104): one
+ *   launch instead of the neg / sub / div / add elementwise passes.  grad_num may be NULL (loss only).
+ * chain_b200_scale_grad: grad[i] *= upstream[0] -- autograd's `grad * objf_grad` (loss.py:85); the kernel returns
+ *   without touching memory when upstream[0] == 1 (a plain loss.backward()). */
+int chain_b200_combine_loss(const float *objf_num_dev, const float *objf_den_dev, float loss_scale,
+                            float *grad_den_dev, const float *grad_num_dev, size_t n, float *loss_dev,
+                            int device, void *stream);
+int chain_b200_scale_grad(float *grad_dev, size_t n, const float *upstream_dev, int device, void *stream);
 
 /* Number of kernel launches the last call on this thread issued (for bench.py's
  * `gpu_launches` accounting). */

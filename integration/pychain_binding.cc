@@ -102,7 +102,7 @@ std::vector<torch::Tensor> ForwardBackward(
     auto ws = torch::empty({(int64_t)ws_bytes}, exp_nnet_output.options().dtype(torch::kByte));
     check_status(chain_b200_den_forward_backward(pk->blob_host.data_ptr(), pk->blob_dev.data_ptr(), 1,
                                                  exp_nnet_output.data_ptr<float>(), len.data_ptr<int64_t>(), B, T, D,
-                                                 leaky_hmm_coefficient, CHAIN_B200_X_IS_EXP, objf.data_ptr<float>(),
+                                                 leaky_hmm_coefficient, CHAIN_B200_X_IS_EXP, /*grad_scale*/ 1.0f, objf.data_ptr<float>(),
                                                  nullptr, grad.data_ptr<float>(), ok.data_ptr<int>(), nullptr,
                                                  ws.data_ptr(), ws_bytes, dev.index(), stream),
                  "chain_b200_den_forward_backward");
@@ -125,7 +125,7 @@ std::vector<torch::Tensor> ForwardBackward(
                                            bt.data_ptr<int>(), bi.data_ptr<int>(), bp.data_ptr<float>(),
                                            lk.data_ptr<float>(), in.data_ptr<float>(), fn.data_ptr<float>(),
                                            exp_nnet_output.data_ptr<float>(), len.data_ptr<int64_t>(), B, T, D, S, K,
-                                           leaky_hmm_coefficient, flags, objf.data_ptr<float>(), nullptr,
+                                           leaky_hmm_coefficient, flags, /*grad_scale*/ 1.0f, objf.data_ptr<float>(), nullptr,
                                            grad.data_ptr<float>(), ok.data_ptr<int>(), nullptr, ws.data_ptr(), ws_bytes,
                                            dev.index(), stream),
                "chain_b200_forward_backward");
@@ -165,7 +165,7 @@ std::vector<torch::Tensor> ForwardBackwardLogDomain(
   check_status(chain_b200_forward_backward_log_domain(
                    ft.data_ptr<int>(), fi.data_ptr<int>(), fp.data_ptr<float>(), bt.data_ptr<int>(), bi.data_ptr<int>(),
                    bp.data_ptr<float>(), in.data_ptr<float>(), fn.data_ptr<float>(), nnet_output.data_ptr<float>(),
-                   len.data_ptr<int64_t>(), B, T, D, S, K, flags, objf.data_ptr<float>(), nullptr,
+                   len.data_ptr<int64_t>(), B, T, D, S, K, flags, /*grad_scale*/ 1.0f, objf.data_ptr<float>(), nullptr,
                    grad.data_ptr<float>(), ok.data_ptr<int>(), nullptr, ws.data_ptr(), ws_bytes, dev.index(),
                    at::cuda::getCurrentCUDAStream().stream()),
                "chain_b200_forward_backward_log_domain");

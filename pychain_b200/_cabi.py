@@ -23,16 +23,18 @@ SIGNATURES = {
     "chain_b200_last_launch_count": (c_int, []),
     "chain_b200_workspace_bytes": (c_size_t, [c_int] * 5 + [c_uint]),
     "chain_b200_forward_backward": (
-        c_int, [c_void_p] * 11 + [c_int] * 5 + [c_float, c_uint] + [c_void_p] * 5 + [c_void_p, c_size_t, c_int, c_void_p]),
+        c_int, [c_void_p] * 11 + [c_int] * 5 + [c_float, c_uint, c_float] + [c_void_p] * 5 + [c_void_p, c_size_t, c_int, c_void_p]),
     "chain_b200_forward_backward_log_domain": (
-        c_int, [c_void_p] * 10 + [c_int] * 5 + [c_uint] + [c_void_p] * 5 + [c_void_p, c_size_t, c_int, c_void_p]),
+        c_int, [c_void_p] * 10 + [c_int] * 5 + [c_uint, c_float] + [c_void_p] * 5 + [c_void_p, c_size_t, c_int, c_void_p]),
     "chain_b200_den_prepare_bytes": (c_int64, [c_void_p] * 4 + [c_int] * 3 + [c_uint]),
     "chain_b200_den_prepare": (c_int, [c_void_p] * 9 + [c_int] * 3 + [c_uint, c_void_p, c_int64]),
     "chain_b200_den_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "chain_b200_den_group_width": (c_int, [c_int] * 4),
     "chain_b200_den_forward_backward": (
-        c_int, [c_void_p] * 2 + [c_int] + [c_void_p] * 2 + [c_int] * 3 + [c_float, c_uint] + [c_void_p] * 5 +
+        c_int, [c_void_p] * 2 + [c_int] + [c_void_p] * 2 + [c_int] * 3 + [c_float, c_uint, c_float] + [c_void_p] * 5 +
         [c_void_p, c_size_t, c_int, c_void_p]),
+    "chain_b200_combine_loss": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
+    "chain_b200_scale_grad": (c_int, [c_void_p, c_size_t, c_void_p, c_int, c_void_p]),
 }
 
 _lib = None

@@ -26,6 +26,7 @@ struct DenParams {
   int B, T, D, S, S_pad, D_pad;
   float coeff;
   unsigned flags;
+  float grad_scale;    // posteriors are multiplied by this as they are written
   float *logp, *grad, *diag;
   float *alpha_ws, *tot_ws;
   int num_groups, use_tma_x;

@@ -40,6 +40,37 @@ __device__ __forceinline__ void mul_fma_x2(float &acc0, float &acc1, float a0, f
       : "f"(a0), "f"(a1), "f"(w), "f"(b0), "f"(b1));
 }
 
+// Shared-memory gather of one element (G floats) as a VOLATILE asm: the four operand loads of a record pair are
+// issued together, ahead of the end-of-slice branch (the compiler would otherwise sink the second record's loads
+// into the branch and expose their latency).
+template <int G> __device__ __forceinline__ void lds_vec(uint32_t addr, float (&v)[G]);
+template <> __device__ __forceinline__ void lds_vec<4>(uint32_t addr, float (&v)[4]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+template <> __device__ __forceinline__ void lds_vec<2>(uint32_t addr, float (&v)[2]) {
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(addr));
+}
+template <> __device__ __forceinline__ void lds_vec<1>(uint32_t addr, float (&v)[1]) {
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(addr));
+}
+
+// acc += a * w * b  /  acc += a * w
+template <int G>
+__device__ __forceinline__ void fma_rec(float (&acc)[G], const float (&a)[G], const float w, const float (&b)[G]) {
+  if constexpr (G % 2 == 0) {
+#pragma unroll
+    for (int g = 0; g < G; g += 2) mul_fma_x2(acc[g], acc[g + 1], a[g], a[g + 1], w, b[g], b[g + 1]);
+  } else {
+#pragma unroll
+    for (int g = 0; g < G; g++) acc[g] = fmaf(a[g] * w, b[g], acc[g]);
+  }
+}
+template <int G>
+__device__ __forceinline__ void fma_rec1(float (&acc)[G], const float (&a)[G], const float w) {
+#pragma unroll
+  for (int g = 0; g < G; g++) acc[g] = fmaf(a[g], w, acc[g]);
+}
+
 template <int G>
 __device__ __forceinline__ void consume_rec(const uint32_t ab, const float w, const float *__restrict__ A,
                                             const float *__restrict__ Bv, float (&acc)[G]) {
@@ -66,7 +97,7 @@ template <int G> __host__ __device__ constexpr int nf2() { return G == 4 ? CHAIN
 // per pair, and they hold 8 fewer operand registers, so their banks are deeper.  (The streams' run-out, 3 *
 // kFifoPairs pairs, covers banks of up to 3 * kFifoPairs pairs.)
 #ifndef CHAIN_B200_NF1_G4
-#define CHAIN_B200_NF1_G4 6
+#define CHAIN_B200_NF1_G4 5
 #endif
 template <int G> __host__ __device__ constexpr int nf1() { return G == 4 ? CHAIN_B200_NF1_G4 : kFifoPairs; }
 
@@ -91,7 +122,9 @@ __device__ __forceinline__ void consume_rec1(const uint32_t ab, const float w, c
 // the depth the streams' run-out is padded for); the gamma pass of G = 4 has the heaviest epilogue and runs one short.
 template <int G, bool L1C, bool ONE, int NF, class Epi>
 __device__ __forceinline__ void sell_pass(const DView &v, const float *__restrict__ A, const float *__restrict__ Bv,
-                                          float *__restrict__ partial, int warp, int lane, Epi &epi) {
+                                          uint32_t amax, uint32_t bmax, float *__restrict__ partial, int warp,
+                                          int lane, Epi &epi) {
+  const uint32_t A_s = smem_u32(A), B_s = ONE ? 0u : smem_u32(Bv);
   const uint4 *sp = reinterpret_cast<const uint4 *>(v.recs + v.warp_info[3 * warp]) + lane;  // [pair][lane]: 2 slots
   const int npairs = (int)v.warp_info[3 * warp + 1];
   uint4 fa[NF], fb[NF];
@@ -103,18 +136,29 @@ __device__ __forceinline__ void sell_pass(const DView &v, const float *__restric
   for (int g = 0; g < G; g++) acc[g] = 0.f;
   // A pair is two arcs, or -- at the end of a slice -- an arc and the lane's ROW-CODE slot (sign bit of its second
   // word; warp-uniform): {row code, -aux}.  The code arrives through the same prefetched stream as the arcs.
+  // The operands of BOTH slots are gathered before the flag is looked at: a row-code slot is not an arc, so its
+  // index fields are clamped into the rows (amax / bmax) and what they fetch is dropped.
   auto process = [&](const uint2 r0, const uint2 r1) {
-    if constexpr (ONE) consume_rec1<G>(r0.x, __uint_as_float(r0.y), A, acc);
-    else consume_rec<G>(r0.x, __uint_as_float(r0.y), A, Bv, acc);
+    float a0[G], a1[G];
+    lds_vec<G>(A_s + (r0.x & 0xffffu) * (G * 4u), a0);
+    lds_vec<G>(A_s + min(r1.x & 0xffffu, amax) * (G * 4u), a1);
+    if constexpr (ONE) {
+      fma_rec1<G>(acc, a0, __uint_as_float(r0.y));
+    } else {
+      float b0[G], b1[G];
+      lds_vec<G>(B_s + (r0.x >> 16) * (G * 4u), b0);
+      lds_vec<G>(B_s + min(r1.x >> 16, bmax) * (G * 4u), b1);
+      fma_rec<G>(acc, a0, __uint_as_float(r0.y), b0);
+      if (!(r1.y & 0x80000000u)) fma_rec<G>(acc, a1, __uint_as_float(r1.y), b1);
+    }
     if (r1.y & 0x80000000u) {
       const int row = (int)r1.x;
       if (row >= 0) epi(row, acc, __uint_as_float(r1.y & 0x7fffffffu));
       else if (row <= -2) st_vec<G>(partial + (size_t)(-2 - row) * G, acc);
 #pragma unroll
       for (int g = 0; g < G; g++) acc[g] = 0.f;
-    } else {
-      if constexpr (ONE) consume_rec1<G>(r1.x, __uint_as_float(r1.y), A, acc);
-      else consume_rec<G>(r1.x, __uint_as_float(r1.y), A, Bv, acc);
+    } else if constexpr (ONE) {
+      fma_rec1<G>(acc, a1, __uint_as_float(r1.y));
     }
   };
   int j = 0;
@@ -321,7 +365,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
           st_vec<G>(aext + (size_t)row * G, acc);
           st_vec<G>(wext + (size_t)row * G, acc);
         };
-        sell_pass<G, L1C, true, nf1<G>()>(views[3], A, nullptr, partial, warp, lane, epi_cls);
+        sell_pass<G, L1C, true, nf1<G>()>(views[3], A, nullptr, R_pad - 1, 0, partial, warp, lane, epi_cls);
         if (p.view[3].n_split) { __syncthreads(); fixup_split<G>(p.view[3], partial, nullptr, epi_cls); }
       }
       __syncthreads();  // x_s complete, xraw free, class sums complete
@@ -334,7 +378,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         for (int g = 0; g < G; g++) part[g] += acc[g];
         st_vec<G>(Bn + (size_t)row * G, acc);
       };
-      sell_pass<G, L1C, false, nf2<G>()>(views[0], A, x_s, partial, warp, lane, epi_fwd);
+      sell_pass<G, L1C, false, nf2<G>()>(views[0], A, x_s, R_pad - 1, D_pad - 1, partial, warp, lane, epi_fwd);
       if (p.view[0].n_split) { __syncthreads(); fixup_split<G>(p.view[0], partial, nullptr, epi_fwd); }
 #pragma unroll
       for (int g = 0; g < G; g++) {
@@ -353,15 +397,28 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         need_z |= (Lg[g] == t);
       }
       float *awt = aws + (size_t)t * R_pad * G;
-      for (int i = tid; i < S; i += DEN_NT) {
-        float v[G];
-        ld_vec<G>(Bn + (size_t)i * G, v);
-        const float l = __ldg(lk + i);
-        const float f = need_z ? __ldg(fin + i) : 0.f;
+      // alpha'(t) = alpha(t) + c tot(t) leaky; spill.  The leaky (and final) probabilities come from L2: four rows'
+      // worth are requested before the first is used.
+      for (int i0 = tid; i0 < S; i0 += 4 * DEN_NT) {
+        float l[4], f[4];
 #pragma unroll
-        for (int g = 0; g < G; g++) { v[g] = fmaf(ct[g], l, v[g]); zp[g] += v[g] * f; }
-        st_vec<G>(Bn + (size_t)i * G, v);
-        st_vec<G>(awt + (size_t)i * G, v);
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u * DEN_NT;
+          l[u] = (i < S) ? __ldg(lk + i) : 0.f;
+          f[u] = (need_z && i < S) ? __ldg(fin + i) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u * DEN_NT;
+          if (i < S) {
+            float v[G];
+            ld_vec<G>(Bn + (size_t)i * G, v);
+#pragma unroll
+            for (int g = 0; g < G; g++) { v[g] = fmaf(ct[g], l[u], v[g]); zp[g] += v[g] * f[u]; }
+            st_vec<G>(Bn + (size_t)i * G, v);
+            st_vec<G>(awt + (size_t)i * G, v);
+          }
+        }
       }
       if (tid == 0) {
         float tv[G];
@@ -446,14 +503,14 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         for (int g = 0; g < G; g++) o[g] = acc[g] * xv[g];
         st_vec<G>(gam_s + (size_t)row * G, o);
       };
-      sell_pass<G, L1C, false, nf2<G>()>(views[2], P, Q, partial, warp, lane, epi_gam);
+      sell_pass<G, L1C, false, nf2<G>()>(views[2], P, Q, R_pad - 1, R_pad - 1, partial, warp, lane, epi_gam);
       if (p.view[2].n_split) { __syncthreads(); fixup_split<G>(p.view[2], partial, nullptr, epi_gam); }
       __syncthreads();  // gamma rows complete; everybody done reading P; bx complete
 
       // ---- beta' pass, class arcs: rows = source states, one operand (bx_c) per arc; the raw sums wait in P
       if (C) {
         auto epi_b2 = [&](int row, const float (&acc)[G], float) { st_vec<G>(P + (size_t)row * G, acc); };
-        sell_pass<G, L1C, true, nf1<G>()>(views[4], Q, nullptr, partial, warp, lane, epi_b2);
+        sell_pass<G, L1C, true, nf1<G>()>(views[4], Q, nullptr, R_pad - 1, 0, partial, warp, lane, epi_b2);
         if (p.view[4].n_split) { __syncthreads(); fixup_split<G>(p.view[4], partial, nullptr, epi_b2); }
         __syncthreads();
       }
@@ -477,7 +534,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         for (int g = 0; g < G; g++) lpart[g] = fmaf(o[g], l, lpart[g]);
         st_vec<G>(P + (size_t)row * G, o);
       };
-      sell_pass<G, L1C, false, nf2<G>()>(views[1], Q, x_s, partial, warp, lane, epi_bwd);
+      sell_pass<G, L1C, false, nf2<G>()>(views[1], Q, x_s, R_pad - 1, D_pad - 1, partial, warp, lane, epi_bwd);
       if (p.view[1].n_split) { __syncthreads(); fixup_split<G>(p.view[1], partial, lk, epi_bwd); }
 #pragma unroll
       for (int g = 0; g < G; g++) {
@@ -493,7 +550,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         ld_vec<G>(gam_s + (size_t)n * G, v);
 #pragma unroll
         for (int g = 0; g < G; g++) {
-          if (b0 + g < p.B) p.grad[((size_t)(b0 + g) * T + t) * D + n] = (t < Lg[g]) ? v[g] : 0.f;
+          if (b0 + g < p.B) p.grad[((size_t)(b0 + g) * T + t) * D + n] = (t < Lg[g]) ? v[g] * p.grad_scale : 0.f;
           gsum[g] += v[g];
         }
       }
@@ -569,8 +626,8 @@ size_t chain_b200_den_workspace_bytes(const void *blob_host, int B, int T) {
 
 int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev, int blob_copies, const float *x,
                                     const int64_t *lengths, int B, int T, int D, float coeff, unsigned flags,
-                                    float *objf, float *logp, float *grad, int32_t *ok, float *diag, void *ws,
-                                    size_t ws_bytes, int device, void *stream_v) {
+                                    float grad_scale, float *objf, float *logp, float *grad, int32_t *ok, float *diag,
+                                    void *ws, size_t ws_bytes, int device, void *stream_v) {
   g_launch_count = 0;
   const BlobHeader *hp = (const BlobHeader *)blob_host;
   if (!hp || !blob_dev) return CHAIN_B200_ERR_INVALID_ARG;
@@ -609,7 +666,7 @@ int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev,
   p.fin = (const float *)(bd + h.off_final);
   p.x = x; p.lengths = lengths;
   p.B = B; p.T = T; p.D = D; p.S = h.S; p.S_pad = h.S_pad; p.D_pad = h.D_pad;
-  p.coeff = coeff; p.flags = flags;
+  p.coeff = coeff; p.flags = flags; p.grad_scale = grad_scale;
   p.logp = logp ? logp : (float *)(base + w.logp);
   p.grad = grad;
   p.diag = (float *)(base + w.diag);

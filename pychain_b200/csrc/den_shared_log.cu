@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
           ld_vec<G>(gam_s + (size_t)n * G, v);
 #pragma unroll
           for (int g = 0; g < G; g++)
-            if (b0 + g < p.B) p.grad[((size_t)(b0 + g) * T + t) * D + n] = (t < Lg[g]) ? v[g] : dead;
+            if (b0 + g < p.B) p.grad[((size_t)(b0 + g) * T + t) * D + n] = (t < Lg[g]) ? (as_log ? v[g] : v[g] * p.grad_scale) : dead;
         }
       }
       if (t == 0) {

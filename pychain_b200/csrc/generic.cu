@@ -17,6 +17,8 @@
 // thread of pdf n, written coalesced and exactly once (the reference uses
 // thresholded atomicAdd / atomicCAS log-add per arc, chain-kernels.cu:53-87,
 // chain-log-domain-kernels.cu:62-75).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace chainb200 {
@@ -33,6 +35,7 @@ struct GenericParams {
   int B, T, D, S, K;
   float coeff;
   unsigned flags;
+  float grad_scale;           // posteriors are multiplied by this as they are written
   float *logp, *grad, *diag;  // diag: [B][2]
   float *alpha_ws, *tot_ws;   // [B][T+1][S], [B][T+1]
   const int32_t *pdf_ptr;     // [Bg][D+1]
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
           g += bufA[r.x & 0xffffu] * __uint_as_float(r.y) * bufB[r.x >> 16];
         }
         const float gam = g * x_s[n] * inv;
-        gr[n] = gam;
+        gr[n] = gam * p.grad_scale;
         gsum += gam;
       }
       // beta' pass: thread owns source state h
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
           lg = m + logf(sm);
           gam = expf(lg);
         }
-        gr[n] = (p.flags & CHAIN_B200_GRAD_AS_LOG) ? lg : gam;
+        gr[n] = (p.flags & CHAIN_B200_GRAD_AS_LOG) ? lg : gam * p.grad_scale;
         gsum += gam;
       }
       for (int h = tid; h < S; h += GEN_NT) {
@@ -447,6 +450,42 @@ void launch_finalize(const float *logp, const float *diag, const int64_t *length
   finalize_kernel<<<1, 256, 0, stream>>>(logp, diag, lengths, B, T, check_ab, objf, ok, diag_out);
 }
 
+// ---------------------------------------------------------------- the tail of pychain/loss.py, fused
+// loss = (objf_den - objf_num) * loss_scale (loss.py:102-104) and grad_den += grad_num (both already carry their
+// +-1/sum(lengths) factor from the kernels' write-out): one launch instead of neg / sub / div / add passes.
+__global__ void __launch_bounds__(256) combine_loss_kernel(const float *__restrict__ objf_num,
+                                                           const float *__restrict__ objf_den, float loss_scale,
+                                                           float *__restrict__ gd, const float *__restrict__ gn,
+                                                           size_t n, size_t nvec, float *__restrict__ loss) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *loss = (*objf_den - *objf_num) * loss_scale;
+  if (!gn) return;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float4 *gd4 = reinterpret_cast<float4 *>(gd);
+  const float4 *gn4 = reinterpret_cast<const float4 *>(gn);
+  for (size_t i = i0; i < nvec; i += stride) {
+    float4 a = gd4[i];
+    const float4 b = __ldg(gn4 + i);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    gd4[i] = a;
+  }
+  for (size_t i = 4 * nvec + i0; i < n; i += stride) gd[i] += gn[i];
+}
+
+// autograd's `input_grad * objf_grad` (loss.py:85).  A plain loss.backward() hands in 1: nothing is touched then.
+__global__ void __launch_bounds__(256) scale_grad_kernel(float *__restrict__ g, size_t n, size_t nvec,
+                                                         const float *__restrict__ upstream) {
+  const float u = __ldg(upstream);
+  if (u == 1.0f) return;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float4 *g4 = reinterpret_cast<float4 *>(g);
+  for (size_t i = i0; i < nvec; i += stride) {
+    float4 a = g4[i];
+    a.x *= u; a.y *= u; a.z *= u; a.w *= u;
+    g4[i] = a;
+  }
+  for (size_t i = 4 * nvec + i0; i < n; i += stride) g[i] *= u;
+}
+
 // ---------------------------------------------------------------- host side
 struct GenericWs {
   size_t alpha, tot, pdf_ptr, pdf_rec, bwd_rec, fwd_rec, logp, diag, rows, total;
@@ -481,8 +520,8 @@ template <bool LOG>
 static int run_generic(const int32_t *ft, const int32_t *fi, const float *fp, const int32_t *bt, const int32_t *bi,
                        const float *bp, const float *leaky, const float *init, const float *fin, const float *x,
                        const int64_t *lengths, int B, int T, int D, int S, int K, float coeff, unsigned flags,
-                       float *objf, float *logp, float *grad, int32_t *ok, float *diag, void *ws, size_t ws_bytes,
-                       int device, void *stream_v) {
+                       float grad_scale, float *objf, float *logp, float *grad, int32_t *ok, float *diag, void *ws,
+                       size_t ws_bytes, int device, void *stream_v) {
   g_launch_count = 0;
   if (B <= 0 || T <= 0 || D <= 0 || S <= 0 || K < 0) return CHAIN_B200_ERR_INVALID_ARG;
   if (!ft || !fi || !fp || !bt || !bi || !bp || !init || !fin || !x || !lengths || !objf || !grad || !ok)
@@ -517,6 +556,7 @@ static int run_generic(const int32_t *ft, const int32_t *fi, const float *fp, co
   GenericParams p;
   p.ft = ft; p.fi = fi; p.bt = bt; p.bi = bi; p.fp = fp; p.bp = bp;
   p.leaky = leaky; p.init = init; p.fin = fin; p.x = x; p.lengths = lengths;
+  p.grad_scale = grad_scale;
   p.B = B; p.T = T; p.D = D; p.S = S; p.K = K; p.coeff = coeff; p.flags = flags;
   p.logp = logp ? logp : (float *)(base + w.logp);
   p.grad = grad;
@@ -577,19 +617,49 @@ size_t chain_b200_workspace_bytes(int B, int T, int D, int S, int K, unsigned fl
 int chain_b200_forward_backward(const int32_t *ft, const int32_t *fi, const float *fp, const int32_t *bt,
                                 const int32_t *bi, const float *bp, const float *leaky, const float *init,
                                 const float *fin, const float *x, const int64_t *lengths, int B, int T, int D, int S,
-                                int K, float coeff, unsigned flags, float *objf, float *logp, float *grad,
-                                int32_t *ok, float *diag, void *ws, size_t ws_bytes, int device, void *stream) {
-  return run_generic<false>(ft, fi, fp, bt, bi, bp, leaky, init, fin, x, lengths, B, T, D, S, K, coeff, flags, objf,
-                            logp, grad, ok, diag, ws, ws_bytes, device, stream);
+                                int K, float coeff, unsigned flags, float grad_scale, float *objf, float *logp,
+                                float *grad, int32_t *ok, float *diag, void *ws, size_t ws_bytes, int device,
+                                void *stream) {
+  return run_generic<false>(ft, fi, fp, bt, bi, bp, leaky, init, fin, x, lengths, B, T, D, S, K, coeff, flags,
+                            grad_scale, objf, logp, grad, ok, diag, ws, ws_bytes, device, stream);
 }
 
 int chain_b200_forward_backward_log_domain(const int32_t *ft, const int32_t *fi, const float *fp, const int32_t *bt,
                                            const int32_t *bi, const float *bp, const float *init, const float *fin,
                                            const float *x, const int64_t *lengths, int B, int T, int D, int S, int K,
-                                           unsigned flags, float *objf, float *logp, float *grad, int32_t *ok,
-                                           float *diag, void *ws, size_t ws_bytes, int device, void *stream) {
+                                           unsigned flags, float grad_scale, float *objf, float *logp, float *grad,
+                                           int32_t *ok, float *diag, void *ws, size_t ws_bytes, int device,
+                                           void *stream) {
   return run_generic<true>(ft, fi, fp, bt, bi, bp, nullptr, init, fin, x, lengths, B, T, D, S, K, 0.f,
-                           flags & ~CHAIN_B200_X_IS_EXP, objf, logp, grad, ok, diag, ws, ws_bytes, device, stream);
+                           flags & ~CHAIN_B200_X_IS_EXP, grad_scale, objf, logp, grad, ok, diag, ws, ws_bytes, device,
+                           stream);
+}
+
+int chain_b200_combine_loss(const float *objf_num, const float *objf_den, float loss_scale, float *grad_den,
+                            const float *grad_num, size_t n, float *loss, int device, void *stream_v) {
+  g_launch_count = 0;
+  if (!objf_num || !objf_den || !loss || (n > 0 && !grad_den)) return CHAIN_B200_ERR_INVALID_ARG;
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return (int)guard.err;
+  const size_t vec = (grad_num && ((uintptr_t)grad_den & 15u) == 0 && ((uintptr_t)grad_num & 15u) == 0) ? n / 4 : 0;
+  const size_t work = grad_num ? (vec ? vec + (n - 4 * vec) : n) : 1;
+  const int grid = (int)std::min<size_t>((work + 255) / 256, (size_t)148 * 8);
+  combine_loss_kernel<<<std::max(grid, 1), 256, 0, (cudaStream_t)stream_v>>>(objf_num, objf_den, loss_scale, grad_den,
+                                                                              grad_num, n, vec, loss);
+  g_launch_count++;
+  return (int)cudaGetLastError();
+}
+
+int chain_b200_scale_grad(float *grad, size_t n, const float *upstream, int device, void *stream_v) {
+  g_launch_count = 0;
+  if (!grad || !upstream) return CHAIN_B200_ERR_INVALID_ARG;
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return (int)guard.err;
+  const size_t vec = (((uintptr_t)grad & 15u) == 0) ? n / 4 : 0;
+  const int grid = (int)std::min<size_t>((std::max<size_t>(vec, n - 4 * vec) + 255) / 256, (size_t)148 * 8);
+  scale_grad_kernel<<<std::max(grid, 1), 256, 0, (cudaStream_t)stream_v>>>(grad, n, vec, upstream);
+  g_launch_count++;
+  return (int)cudaGetLastError();
 }
 
 }  // extern "C"

@@ -15,7 +15,8 @@ import torch
 from . import _cabi
 from ._cabi import GRAPH_SHARED, X_IS_EXP, CLAMP_X, GRAD_AS_LOG, ChainB200Error
 
-__all__ = ["forward_backward_prob", "forward_backward_log", "prepare_den_graph", "launch_count", "Result"]
+__all__ = ["forward_backward_prob", "forward_backward_log", "prepare_den_graph", "launch_count", "Result",
+           "combine_loss", "scale_grad_"]
 
 _GRAPH_NAMES_PROB = ("forward_transitions", "forward_transition_indices", "forward_transition_probs",
                      "backward_transitions", "backward_transition_indices", "backward_transition_probs",
@@ -125,7 +126,7 @@ def _launch_stream(dev, stream):
 
 
 def _run_generic(log_domain, graph_tensors, x, lengths, num_states, leaky_coefficient, flags, want_logp=True,
-                 stream=None):
+                 stream=None, grad_scale=1.0):
     global _launches
     lib = _cabi.lib()
     what = "nnet_output" if log_domain else "exp_nnet_output"
@@ -150,12 +151,12 @@ def _run_generic(log_domain, graph_tensors, x, lengths, num_states, leaky_coeffi
     tstream, cstream = _launch_stream(dev, stream)
     if log_domain:
         st = lib.chain_b200_forward_backward_log_domain(
-            *[_ptr(t) for t in g], _ptr(x), _ptr(ldev), B, T, D, S, K, flags,
+            *[_ptr(t) for t in g], _ptr(x), _ptr(ldev), B, T, D, S, K, flags, float(grad_scale),
             _ptr(objf), _ptr(logp), _ptr(grad), _ptr(ok), _ptr(diag), _ptr(ws), ws_bytes, dev.index or 0, cstream)
         _cabi.check(st, "chain_b200_forward_backward_log_domain")
     else:
         st = lib.chain_b200_forward_backward(
-            *[_ptr(t) for t in g], _ptr(x), _ptr(ldev), B, T, D, S, K, float(leaky_coefficient), flags,
+            *[_ptr(t) for t in g], _ptr(x), _ptr(ldev), B, T, D, S, K, float(leaky_coefficient), flags, float(grad_scale),
             _ptr(objf), _ptr(logp), _ptr(grad), _ptr(ok), _ptr(diag), _ptr(ws), ws_bytes, dev.index or 0, cstream)
         _cabi.check(st, "chain_b200_forward_backward")
     _launches += lib.chain_b200_last_launch_count()
@@ -219,7 +220,7 @@ def prepare_den_graph(graph_tensors, num_states, D, device, log_domain=False, ba
     return prep
 
 
-def _run_den_shared(prep, x, lengths, leaky_coefficient, flags, stream=None):
+def _run_den_shared(prep, x, lengths, leaky_coefficient, flags, stream=None, grad_scale=1.0):
     global _launches
     lib = _cabi.lib()
     _require_cuda(x, "exp_nnet_output" if flags & X_IS_EXP else "nnet_output")
@@ -238,7 +239,7 @@ def _run_den_shared(prep, x, lengths, leaky_coefficient, flags, stream=None):
     tstream, cstream = _launch_stream(dev, stream)
     st = lib.chain_b200_den_forward_backward(
         _ptr(prep.blob_host), _ptr(prep.blob_dev), prep.copies, _ptr(x), _ptr(ldev), B, T, D, float(leaky_coefficient), flags,
-        _ptr(objf), _ptr(logp), _ptr(grad), _ptr(ok), _ptr(diag), _ptr(ws), ws_bytes, dev.index or 0, cstream)
+        float(grad_scale), _ptr(objf), _ptr(logp), _ptr(grad), _ptr(ok), _ptr(diag), _ptr(ws), ws_bytes, dev.index or 0, cstream)
     _cabi.check(st, "chain_b200_den_forward_backward")
     _launches += lib.chain_b200_last_launch_count()
     if stream is not None:
@@ -304,24 +305,26 @@ def _try_packed(run, fallback):
 
 
 def forward_backward_prob(graph_tensors, x, lengths, num_states, leaky_coefficient=1e-5, x_is_exp=True, clamp=False,
-                          path=None, stream=None):
+                          path=None, stream=None, grad_scale=1.0):
     """Probability-domain (denominator) forward-backward.  `graph_tensors` in
-    _GRAPH_NAMES_PROB order, reference layout."""
+    _GRAPH_NAMES_PROB order, reference layout.  The posteriors are written multiplied by `grad_scale`."""
     flags = (X_IS_EXP if x_is_exp else 0) | (CLAMP_X if clamp else 0)
     path = path or DEN_PATH
     B = x.size(0)
-    generic = lambda: _run_generic(False, graph_tensors, x, lengths, num_states, leaky_coefficient, flags, stream=stream)  # noqa: E731
+    generic = lambda: _run_generic(False, graph_tensors, x, lengths, num_states, leaky_coefficient, flags,  # noqa: E731
+                                   stream=stream, grad_scale=grad_scale)
     if path != "generic" and _shared_fits(int(num_states), int(x.size(2))):
         rows, ckey = _shared_rows(graph_tensors, B)
         if rows is not None:
             def packed():
                 prep = prepare_den_graph(rows, num_states, x.size(2), x.device, batch_size=B, content_key=ckey)
-                return _run_den_shared(prep, x, lengths, leaky_coefficient, flags, stream=stream)
+                return _run_den_shared(prep, x, lengths, leaky_coefficient, flags, stream=stream, grad_scale=grad_scale)
             return _try_packed(packed, generic)
     return generic()
 
 
-def forward_backward_log(graph_tensors, x, lengths, num_states, grad_as_log=True, clamp=False, path=None, stream=None):
+def forward_backward_log(graph_tensors, x, lengths, num_states, grad_as_log=True, clamp=False, path=None, stream=None,
+                         grad_scale=1.0):
     """Log-domain (numerator) forward-backward.  `graph_tensors` in _GRAPH_NAMES_LOG order.
     A graph shared by the whole batch (stride-0 views) with >= 256 arcs runs on the packed
     shared-graph kernels, per-utterance graphs on the general kernel."""
@@ -329,7 +332,8 @@ def forward_backward_log(graph_tensors, x, lengths, num_states, grad_as_log=True
     path = path or DEN_PATH
     S, K = int(num_states), int(graph_tensors[0].size(1))
     B = x.size(0)
-    generic = lambda: _run_generic(True, graph_tensors, x, lengths, num_states, 0.0, flags, stream=stream)  # noqa: E731
+    generic = lambda: _run_generic(True, graph_tensors, x, lengths, num_states, 0.0, flags, stream=stream,  # noqa: E731
+                                   grad_scale=grad_scale)
     if (path != "generic" and B > 1 and K >= 256 and S <= 32767 and x.size(2) <= 32767
             and _shared_fits(S, int(x.size(2)))):
         rows, ckey = _shared_rows(graph_tensors, B)
@@ -337,6 +341,35 @@ def forward_backward_log(graph_tensors, x, lengths, num_states, grad_as_log=True
             def packed():
                 prep = prepare_den_graph(rows, num_states, x.size(2), x.device, log_domain=True, batch_size=B,
                                          content_key=ckey)
-                return _run_den_shared(prep, x, lengths, 0.5, flags, stream=stream)
+                return _run_den_shared(prep, x, lengths, 0.5, flags, stream=stream, grad_scale=grad_scale)
             return _try_packed(packed, generic)
     return generic()
+
+
+def combine_loss(num, den, loss_scale, with_grad=True):
+    """The tail of `ChainLoss.forward` (loss.py:102-104) in one launch: loss = (den.objf - num.objf) * loss_scale and
+    den.grad += num.grad (both already scaled by the kernels).  Returns the 0-dim loss tensor."""
+    global _launches
+    lib = _cabi.lib()
+    loss = torch.empty((), dtype=torch.float32, device=den.objf.device)
+    cur = torch.cuda.current_stream(loss.device)
+    st = lib.chain_b200_combine_loss(_ptr(num.objf), _ptr(den.objf), float(loss_scale), _ptr(den.grad),
+                                     _ptr(num.grad) if with_grad else None, den.grad.numel(), _ptr(loss),
+                                     loss.device.index or 0, ctypes.c_void_p(cur.cuda_stream))
+    _cabi.check(st, "chain_b200_combine_loss")
+    _launches += lib.chain_b200_last_launch_count()
+    return loss
+
+
+def scale_grad_(grad, upstream):
+    """grad *= upstream (a 0-dim device tensor) in place; a no-op on the device when upstream == 1."""
+    global _launches
+    lib = _cabi.lib()
+    if not upstream.is_cuda or upstream.dtype != torch.float32:
+        upstream = upstream.to(device=grad.device, dtype=torch.float32)
+    cur = torch.cuda.current_stream(grad.device)
+    st = lib.chain_b200_scale_grad(_ptr(grad), grad.numel(), _ptr(upstream), grad.device.index or 0,
+                                   ctypes.c_void_p(cur.cuda_stream))
+    _cabi.check(st, "chain_b200_scale_grad")
+    _launches += lib.chain_b200_last_launch_count()
+    return grad

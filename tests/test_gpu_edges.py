@@ -80,11 +80,11 @@ def test_error_codes_not_crashes(cuda):
     out = torch.empty(1, device=cuda); grad = torch.empty_like(xd); ok = torch.empty(1, dtype=torch.int32, device=cuda)
     ld = lengths.to(cuda)
     p = lambda t: ctypes.c_void_p(t.data_ptr())
-    st = lib.chain_b200_forward_backward(*[p(t) for t in dev], p(xd), p(ld), 2, 5, 8, 10, 30, 1e-5, _cabi.GRAPH_SHARED,
+    st = lib.chain_b200_forward_backward(*[p(t) for t in dev], p(xd), p(ld), 2, 5, 8, 10, 30, 1e-5, _cabi.GRAPH_SHARED, 1.0,
                                          p(out), None, p(grad), p(ok), None, None, 0, 0, None)
     assert st == _cabi.ERR_WORKSPACE
     # more pdfs than the pdf-sort kernel can count on chip -> UNSUPPORTED, not a launch failure
-    assert lib.chain_b200_forward_backward(*[p(t) for t in dev], p(xd), p(ld), 2, 5, 60000, 10, 30, 1e-5, _cabi.GRAPH_SHARED,
+    assert lib.chain_b200_forward_backward(*[p(t) for t in dev], p(xd), p(ld), 2, 5, 60000, 10, 30, 1e-5, _cabi.GRAPH_SHARED, 1.0,
                                            p(out), None, p(grad), p(ok), None, p(grad), 1 << 40, 0, None) == _cabi.ERR_UNSUPPORTED
     torch.cuda.synchronize()
 
