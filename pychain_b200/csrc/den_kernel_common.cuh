@@ -59,6 +59,21 @@ template <> __device__ __forceinline__ void st_vec<2>(float *p, const float (&v)
 }
 template <> __device__ __forceinline__ void st_vec<1>(float *p, const float (&v)[1]) { *p = v[0]; }
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p);
+// Shared-memory gather of one element (G floats) as a VOLATILE asm: the four operand loads of a record pair are
+// issued together, ahead of the end-of-slice branch (the compiler would otherwise sink the second record's loads
+// into the branch and expose their latency).
+template <int G> __device__ __forceinline__ void lds_vec(uint32_t addr, float (&v)[G]);
+template <> __device__ __forceinline__ void lds_vec<4>(uint32_t addr, float (&v)[4]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+template <> __device__ __forceinline__ void lds_vec<2>(uint32_t addr, float (&v)[2]) {
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(addr));
+}
+template <> __device__ __forceinline__ void lds_vec<1>(uint32_t addr, float (&v)[1]) {
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(addr));
+}
+
 // one lane's PAIR of records (16 bytes); a warp reads 512 contiguous bytes
 template <bool L1C>
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {

@@ -40,20 +40,6 @@ __device__ __forceinline__ void mul_fma_x2(float &acc0, float &acc1, float a0, f
       : "f"(a0), "f"(a1), "f"(w), "f"(b0), "f"(b1));
 }
 
-// Shared-memory gather of one element (G floats) as a VOLATILE asm: the four operand loads of a record pair are
-// issued together, ahead of the end-of-slice branch (the compiler would otherwise sink the second record's loads
-// into the branch and expose their latency).
-template <int G> __device__ __forceinline__ void lds_vec(uint32_t addr, float (&v)[G]);
-template <> __device__ __forceinline__ void lds_vec<4>(uint32_t addr, float (&v)[4]) {
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
-}
-template <> __device__ __forceinline__ void lds_vec<2>(uint32_t addr, float (&v)[2]) {
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(addr));
-}
-template <> __device__ __forceinline__ void lds_vec<1>(uint32_t addr, float (&v)[1]) {
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(addr));
-}
-
 // acc += a * w * b  /  acc += a * w
 template <int G>
 __device__ __forceinline__ void fma_rec(float (&acc)[G], const float (&a)[G], const float w, const float (&b)[G]) {
