@@ -42,7 +42,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg4")
-    ap.add_argument("--variant", default="uniform", choices=["uniform", "skew", "biphone"])
+    ap.add_argument("--variant", default="biphone", choices=["uniform", "skew", "biphone"],
+                    help="structure of the synthetic denominator FST.  biphone (default; BASELINE.json names cfg4 'biphone "
+                         "denominator'): states = phone pairs, the pdf of an arc is a function of its destination, as in "
+                         "chain graphs.  uniform: every arc draws its pdf at random (the worst case: no (dst,pdf) class "
+                         "has two arcs).  skew: uniform pdfs, Zipf in-degrees.  The default run also times the other two.")
+    ap.add_argument("--no-other-variants", action="store_true", help="skip the short timing of the other FST variants")
     ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA path")
@@ -473,6 +478,33 @@ def main():
         except Exception as ex:  # the baseline must never take the bench line down
             cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)[:300]}
 
+    # -------- the other structures of the synthetic FST, same sizes, same step, short runs (context for the headline)
+    other = None
+    if world == 1 and mode == "den" and not a.no_other_variants:
+        other = {}
+        for var in ("uniform", "skew", "biphone"):
+            if var == a.variant:
+                continue
+            try:
+                sp2 = synth.workload_spec(a.config, var)
+                sp2["B"] = B
+                g2 = synth.build_workload(sp2, 0, 1)[0]
+                gb2 = ChainGraphBatch(g2, B)
+                gt2 = tuple(getattr(gb2, n) for n in engine._GRAPH_NAMES_PROB)
+                for _ in range(3):
+                    engine.forward_backward_prob(gt2, x_dev, lengths, S, 1e-5, x_is_exp=False, clamp=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(5):
+                    r2 = engine.forward_backward_prob(gt2, x_dev, lengths, S, 1e-5, x_is_exp=False, clamp=True)
+                e1.record()
+                torch.cuda.synchronize()
+                ms2 = e0.elapsed_time(e1) / 5
+                other[var] = {"ms_per_step": ms2, "value": frames / (ms2 * 1e-3), "unit": UNIT, "steps": 5,
+                              "roofline_frac": alg_bytes / (ms2 * 1e-3) / 1e9 / peak, "ok": int(r2.ok.item())}
+            except Exception as ex:
+                other[var] = {"error": repr(ex)[:200]}
+
     # -------- the reference's own CUDA path on this GPU, same tensors
     ref_cuda = None
     if not a.no_ref_cuda and world == 1 and mode in ("den", "logden"):
@@ -495,7 +527,8 @@ def main():
                        "network's backward, as in training; pcie_ceiling = frames / (H2D of one step's x alone)" % (
                            "ChainLoss.forward + backward" if mode == "loss" else "ChainFunction.apply")},
         "gpu_launches": launches,
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_cuda": ref_cuda, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_cuda": ref_cuda, "other_variants": other,
+        "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

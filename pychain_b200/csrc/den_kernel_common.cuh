@@ -74,6 +74,17 @@ template <> __device__ __forceinline__ void lds_vec<1>(uint32_t addr, float (&v)
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(addr));
 }
 
+template <int G> __device__ __forceinline__ void sts_vec(uint32_t addr, const float (&v)[G]);
+template <> __device__ __forceinline__ void sts_vec<4>(uint32_t addr, const float (&v)[4]) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+template <> __device__ __forceinline__ void sts_vec<2>(uint32_t addr, const float (&v)[2]) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v[0]), "f"(v[1]) : "memory");
+}
+template <> __device__ __forceinline__ void sts_vec<1>(uint32_t addr, const float (&v)[1]) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v[0]) : "memory");
+}
+
 // one lane's PAIR of records (16 bytes); a warp reads 512 contiguous bytes
 template <bool L1C>
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {

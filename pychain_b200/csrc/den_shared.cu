@@ -79,6 +79,14 @@ __device__ __forceinline__ void consume_rec(const uint32_t ab, const float w, co
 #define CHAIN_B200_NF2_G4 (kFifoPairs - 1)
 #endif
 template <int G> __host__ __device__ constexpr int nf2() { return G == 4 ? CHAIN_B200_NF2_G4 : kFifoPairs; }
+#ifndef CHAIN_B200_NF2A_G4
+#define CHAIN_B200_NF2A_G4 CHAIN_B200_NF2_G4
+#endif
+template <int G> __host__ __device__ constexpr int nf2a() { return G == 4 ? CHAIN_B200_NF2A_G4 : kFifoPairs; }  // alpha pass
+#ifndef CHAIN_B200_PAIR_FENCE
+#define CHAIN_B200_PAIR_FENCE 1
+#endif
+constexpr bool kPairFence = CHAIN_B200_PAIR_FENCE != 0;
 // One-operand passes (class views) have cheap pairs: a bank must cover the L2 latency with fewer cycles of work
 // per pair, and they hold 8 fewer operand registers, so their banks are deeper.  (The streams' run-out, 3 *
 // kFifoPairs pairs, covers banks of up to 3 * kFifoPairs pairs.)
@@ -96,23 +104,29 @@ __device__ __forceinline__ void consume_rec1(const uint32_t ab, const float w, c
   for (int g = 0; g < G; g++) acc[g] = fmaf(a[g], w, acc[g]);
 }
 
-// One SELL pass: every lane owns one row (or sub-row) of each of its warp's slices and
-// accumulates sum_k w_k * A[a_k][g] * Bv[b_k][g] over the row's records.  The warp's
-// records are one contiguous stream consumed in pairs by a flat counted loop.  Two register
-// banks of kFifoPairs pairs alternate: while one bank is consumed the other is being filled
-// (its previous contents are dead), so kFifoPairs pairs of record loads are always in
-// flight to cover the L2 latency and no load ever lands in a register that is still live.
-// The sign bit of the second weight of a pair ends a slice: run the epilogue for the lane's
-// row and move to the next row code (fetched two slices ahead).
-// ONE: the records carry one operand (consume_rec1), Bv is unused.  NF: record pairs per register bank (<= NF,
-// the depth the streams' run-out is padded for); the gamma pass of G = 4 has the heaviest epilogue and runs one short.
+// One SELL pass: every lane owns one row (or sub-row) of each of its warp's slices and accumulates
+// sum_k w_k * A[a_k][g] * Bv[b_k][g] over the row's records (ONE: sum_k w_k * A[a_k][g]).  The warp's slots are one
+// contiguous stream consumed in pairs by a flat counted loop; two register banks of NF pairs alternate: while one
+// bank is consumed the other is being filled, so NF pairs of 128-bit record loads are always in flight per lane.
+//
+// The pass is a real function (__noinline__): the kernel around it keeps some forty values alive across a pass
+// (pointers, sizes, loop state), and inlined they compete with the record banks for the 128 registers a 512-thread
+// CTA allows -- ptxas then spills bank entries right after their loads, which serialises the warp on the L2 latency
+// of the record stream, the very thing the banks exist to hide.  As a callee the loop has the register file to itself
+// (the caller's state is saved once per pass) and the banks can be as deep as the latency asks.
+// The epilogue is a small functor passed and returned BY VALUE (its accumulators live in the callee's registers).
+#ifndef CHAIN_B200_INLINE_PASS
+#define CHAIN_B200_INLINE_PASS 0
+#endif
+#if CHAIN_B200_INLINE_PASS
+#define CHAIN_B200_PASS_ATTR __forceinline__
+#else
+#define CHAIN_B200_PASS_ATTR __noinline__
+#endif
 template <int G, bool L1C, bool ONE, int NF, class Epi>
-__device__ __forceinline__ void sell_pass(const DView &v, const float *__restrict__ A, const float *__restrict__ Bv,
-                                          uint32_t amax, uint32_t bmax, float *__restrict__ partial, int warp,
-                                          int lane, Epi &epi) {
-  const uint32_t A_s = smem_u32(A), B_s = ONE ? 0u : smem_u32(Bv);
-  const uint4 *sp = reinterpret_cast<const uint4 *>(v.recs + v.warp_info[3 * warp]) + lane;  // [pair][lane]: 2 slots
-  const int npairs = (int)v.warp_info[3 * warp + 1];
+__device__ CHAIN_B200_PASS_ATTR Epi sell_pass(const uint4 *__restrict__ sp, const int npairs, const uint32_t A_s,
+                                      const uint32_t B_s, const uint32_t amax, const uint32_t bmax,
+                                      const uint32_t part_s, Epi epi) {
   uint4 fa[NF], fb[NF];
 #pragma unroll
   for (int d = 0; d < NF; d++) fa[d] = ldg_stream<L1C>(sp + d * 32);
@@ -125,13 +139,16 @@ __device__ __forceinline__ void sell_pass(const DView &v, const float *__restric
   // The operands of BOTH slots are gathered before the flag is looked at: a row-code slot is not an arc, so its
   // index fields are clamped into the rows (amax / bmax) and what they fetch is dropped.
   auto process = [&](const uint2 r0, const uint2 r1) {
-    float a0[G], a1[G];
-    lds_vec<G>(A_s + (r0.x & 0xffffu) * (G * 4u), a0);
-    lds_vec<G>(A_s + min(r1.x & 0xffffu, amax) * (G * 4u), a1);
     if constexpr (ONE) {
+      float a0[G], a1[G];
+      lds_vec<G>(A_s + (r0.x & 0xffffu) * (G * 4u), a0);
+      lds_vec<G>(A_s + min(r1.x & 0xffffu, amax) * (G * 4u), a1);
       fma_rec1<G>(acc, a0, __uint_as_float(r0.y));
+      if (!(r1.y & 0x80000000u)) fma_rec1<G>(acc, a1, __uint_as_float(r1.y));
     } else {
-      float b0[G], b1[G];
+      float a0[G], a1[G], b0[G], b1[G];
+      lds_vec<G>(A_s + (r0.x & 0xffffu) * (G * 4u), a0);
+      lds_vec<G>(A_s + min(r1.x & 0xffffu, amax) * (G * 4u), a1);
       lds_vec<G>(B_s + (r0.x >> 16) * (G * 4u), b0);
       lds_vec<G>(B_s + min(r1.x >> 16, bmax) * (G * 4u), b1);
       fma_rec<G>(acc, a0, __uint_as_float(r0.y), b0);
@@ -140,11 +157,16 @@ __device__ __forceinline__ void sell_pass(const DView &v, const float *__restric
     if (r1.y & 0x80000000u) {
       const int row = (int)r1.x;
       if (row >= 0) epi(row, acc, __uint_as_float(r1.y & 0x7fffffffu));
-      else if (row <= -2) st_vec<G>(partial + (size_t)(-2 - row) * G, acc);
+      else if (row <= -2) sts_vec<G>(part_s + (uint32_t)(-2 - row) * (G * 4u), acc);
 #pragma unroll
       for (int g = 0; g < G; g++) acc[g] = 0.f;
-    } else if constexpr (ONE) {
-      fma_rec1<G>(acc, a1, __uint_as_float(r1.y));
+    }
+    if constexpr (kPairFence) {
+      // keep the gathers of the next pair behind this pair's arithmetic: the operand registers of ONE pair are live at
+      // a time, the rest of the register file holds record banks (the LDS latency this exposes is covered by the other
+      // 15 warps; the L2 latency of the record stream is not)
+#pragma unroll
+      for (int g = 0; g < G; g++) asm volatile("" : "+f"(acc[g]));
     }
   };
   int j = 0;
@@ -175,7 +197,67 @@ __device__ __forceinline__ void sell_pass(const DView &v, const float *__restric
         if (NF + d < rem) process(make_uint2(fb[d].x, fb[d].y), make_uint2(fb[d].z, fb[d].w));
     }
   }
+  return epi;
 }
+
+// Launch one pass for this warp: stream start / length of view `v`.
+template <int G, bool L1C, bool ONE, int NF, class Epi>
+__device__ __forceinline__ Epi run_pass(const DView &v, uint32_t A_s, uint32_t B_s, uint32_t amax, uint32_t bmax,
+                                        uint32_t part_s, int warp, int lane, Epi epi) {
+  const uint4 *sp = reinterpret_cast<const uint4 *>(v.recs + v.warp_info[3 * warp]) + lane;  // [pair][lane]: 2 slots
+  return sell_pass<G, L1C, ONE, NF, Epi>(sp, (int)v.warp_info[3 * warp + 1], A_s, B_s, amax, bmax, part_s, epi);
+}
+
+// ---- the epilogues of the five passes: what happens to a finished row --------------------------------------
+template <int G> struct EpiClass {   // view 3: class sum -> extension of the state row (shared) + its spill (global)
+  uint32_t ext_s; float *ext_g;
+  __device__ __forceinline__ void operator()(int row, const float (&acc)[G], float) {
+    sts_vec<G>(ext_s + (uint32_t)row * (G * 4u), acc);
+    st_vec<G>(ext_g + (size_t)row * G, acc);
+  }
+};
+template <int G> struct EpiAlpha {   // view 0: alpha(t,row), and its contribution to tot(t)
+  uint32_t out_s; float part[G];
+  __device__ __forceinline__ void operator()(int row, const float (&acc)[G], float) {
+#pragma unroll
+    for (int g = 0; g < G; g++) part[g] += acc[g];
+    sts_vec<G>(out_s + (uint32_t)row * (G * 4u), acc);
+  }
+};
+template <int G> struct EpiGamma {   // view 2: gamma(t,pdf) = x(t,pdf)/tot(t) * sum
+  uint32_t xs_s, gam_s;
+  __device__ __forceinline__ void operator()(int row, const float (&acc)[G], float) {
+    float xv[G], o[G];
+    lds_vec<G>(xs_s + (uint32_t)row * (G * 4u), xv);
+#pragma unroll
+    for (int g = 0; g < G; g++) o[g] = acc[g] * xv[g];
+    sts_vec<G>(gam_s + (uint32_t)row * (G * 4u), o);
+  }
+};
+template <int G> struct EpiStore {   // view 4: raw class-arc sums of beta', parked in P
+  uint32_t out_s;
+  __device__ __forceinline__ void operator()(int row, const float (&acc)[G], float) {
+    sts_vec<G>(out_s + (uint32_t)row * (G * 4u), acc);
+  }
+};
+template <int G> struct EpiBeta {    // view 1: beta'(t,row) (+ what view 4 parked), and sum_i beta'(t,i) leaky_i
+  uint32_t out_s; float lpart[G];
+  __device__ __forceinline__ void operator()(int code, const float (&acc)[G], float l /* leaky(row) */) {
+    const uint32_t at = out_s + (uint32_t)(code & (kRowExtraFlag - 1)) * (G * 4u);
+    float o[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) o[g] = acc[g];
+    if (code & kRowExtraFlag) {  // this state also has class arcs
+      float e[G];
+      lds_vec<G>(at, e);
+#pragma unroll
+      for (int g = 0; g < G; g++) o[g] += e[g];
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) lpart[g] = fmaf(o[g], l, lpart[g]);
+    sts_vec<G>(at, o);
+  }
+};
 
 // Rows that were split: add the sub-row partial sums (fixed order) and run the epilogue.  `aux_tab`: the per-row
 // float the row-code slot would have carried (leaky probabilities for the beta' pass), or null.
@@ -220,6 +302,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
   float *xraw = x_s + (size_t)D_pad * G;
   float *gam_s = xraw + (size_t)D_pad * G;
   float *partial = gam_s + (size_t)D_pad * G;
+  const uint32_t part_sa = smem_u32(partial);
   const float *__restrict__ lk = p.leaky;
   const float *__restrict__ ini = p.init;
   const float *__restrict__ fin = p.fin;
@@ -346,30 +429,23 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       if (C) {
         // class sums A_c(t-1) = sum_{arcs of class c} alpha'(t-1,src) * w: one operand per arc.  They extend the
         // state row (virtual states S_pad + c) and are spilled with it: the backward pass needs them again.
-        float *aext = A + (size_t)S_pad * G, *wext = aws + ((size_t)(t - 1) * R_pad + S_pad) * G;
-        auto epi_cls = [&](int row, const float (&acc)[G], float) {
-          st_vec<G>(aext + (size_t)row * G, acc);
-          st_vec<G>(wext + (size_t)row * G, acc);
-        };
-        sell_pass<G, L1C, true, nf1<G>()>(views[3], A, nullptr, R_pad - 1, 0, partial, warp, lane, epi_cls);
+        EpiClass<G> epi_cls{smem_u32(A + (size_t)S_pad * G), aws + ((size_t)(t - 1) * R_pad + S_pad) * G};
+        epi_cls = run_pass<G, L1C, true, nf1<G>()>(views[3], smem_u32(A), 0u, R_pad - 1, 0, part_sa, warp, lane, epi_cls);
         if (p.view[3].n_split) { __syncthreads(); fixup_split<G>(p.view[3], partial, nullptr, epi_cls); }
       }
       __syncthreads();  // x_s complete, xraw free, class sums complete
       if (t < Lmax) issue_x(t);
-      float part[G];
+      EpiAlpha<G> epi_fwd;
+      epi_fwd.out_s = smem_u32(Bn);
 #pragma unroll
-      for (int g = 0; g < G; g++) part[g] = 0.f;
-      auto epi_fwd = [&](int row, const float (&acc)[G], float) {
-#pragma unroll
-        for (int g = 0; g < G; g++) part[g] += acc[g];
-        st_vec<G>(Bn + (size_t)row * G, acc);
-      };
-      sell_pass<G, L1C, false, nf2<G>()>(views[0], A, x_s, R_pad - 1, D_pad - 1, partial, warp, lane, epi_fwd);
+      for (int g = 0; g < G; g++) epi_fwd.part[g] = 0.f;
+      epi_fwd = run_pass<G, L1C, false, nf2a<G>()>(views[0], smem_u32(A), smem_u32(x_s), R_pad - 1, D_pad - 1, part_sa,
+                                                   warp, lane, epi_fwd);
       if (p.view[0].n_split) { __syncthreads(); fixup_split<G>(p.view[0], partial, nullptr, epi_fwd); }
 #pragma unroll
       for (int g = 0; g < G; g++) {
-        part[g] = warp_sum(part[g]);
-        if (lane == 0) red[warp * G + g] = part[g];
+        const float ps = warp_sum(epi_fwd.part[g]);
+        if (lane == 0) red[warp * G + g] = ps;
       }
       __syncthreads();  // alpha(t) rows + partial sums visible; everybody done reading A
       bool need_z = false;
@@ -482,50 +558,32 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       }
 
       // ---- gamma pass: rows = pdfs; gamma(t,n) = x(t,n)/tot(t) * sum alpha'(src) p beta(dst)
-      auto epi_gam = [&](int row, const float (&acc)[G], float) {
-        float xv[G], o[G];
-        ld_vec<G>(x_s + (size_t)row * G, xv);
-#pragma unroll
-        for (int g = 0; g < G; g++) o[g] = acc[g] * xv[g];
-        st_vec<G>(gam_s + (size_t)row * G, o);
-      };
-      sell_pass<G, L1C, false, nf2<G>()>(views[2], P, Q, R_pad - 1, R_pad - 1, partial, warp, lane, epi_gam);
+      EpiGamma<G> epi_gam{smem_u32(x_s), smem_u32(gam_s)};
+      epi_gam = run_pass<G, L1C, false, nf2<G>()>(views[2], smem_u32(P), smem_u32(Q), R_pad - 1, R_pad - 1, part_sa,
+                                                   warp, lane, epi_gam);
       if (p.view[2].n_split) { __syncthreads(); fixup_split<G>(p.view[2], partial, nullptr, epi_gam); }
       __syncthreads();  // gamma rows complete; everybody done reading P; bx complete
 
       // ---- beta' pass, class arcs: rows = source states, one operand (bx_c) per arc; the raw sums wait in P
       if (C) {
-        auto epi_b2 = [&](int row, const float (&acc)[G], float) { st_vec<G>(P + (size_t)row * G, acc); };
-        sell_pass<G, L1C, true, nf1<G>()>(views[4], Q, nullptr, R_pad - 1, 0, partial, warp, lane, epi_b2);
+        EpiStore<G> epi_b2{smem_u32(P)};
+        epi_b2 = run_pass<G, L1C, true, nf1<G>()>(views[4], smem_u32(Q), 0u, R_pad - 1, 0, part_sa, warp, lane, epi_b2);
         if (p.view[4].n_split) { __syncthreads(); fixup_split<G>(p.view[4], partial, nullptr, epi_b2); }
         __syncthreads();
       }
 
       // ---- beta' pass: rows = source states; beta'(t,i) = sum p beta(t+1,dst) x(t,pdf) / tot(t)
-      float lpart[G];
+      EpiBeta<G> epi_bwd;
+      epi_bwd.out_s = smem_u32(P);
 #pragma unroll
-      for (int g = 0; g < G; g++) lpart[g] = 0.f;
-      auto epi_bwd = [&](int code, const float (&acc)[G], float l /* leaky(row), from the row-code slot */) {
-        const int row = code & (kRowExtraFlag - 1);
-        float o[G];
-#pragma unroll
-        for (int g = 0; g < G; g++) o[g] = acc[g];
-        if (code & kRowExtraFlag) {  // this state also has class arcs: view 4 left their sum in P[row]
-          float e[G];
-          ld_vec<G>(P + (size_t)row * G, e);
-#pragma unroll
-          for (int g = 0; g < G; g++) o[g] += e[g];
-        }
-#pragma unroll
-        for (int g = 0; g < G; g++) lpart[g] = fmaf(o[g], l, lpart[g]);
-        st_vec<G>(P + (size_t)row * G, o);
-      };
-      sell_pass<G, L1C, false, nf2<G>()>(views[1], Q, x_s, R_pad - 1, D_pad - 1, partial, warp, lane, epi_bwd);
+      for (int g = 0; g < G; g++) epi_bwd.lpart[g] = 0.f;
+      epi_bwd = run_pass<G, L1C, false, nf2<G>()>(views[1], smem_u32(Q), smem_u32(x_s), R_pad - 1, D_pad - 1, part_sa,
+                                                   warp, lane, epi_bwd);
       if (p.view[1].n_split) { __syncthreads(); fixup_split<G>(p.view[1], partial, lk, epi_bwd); }
 #pragma unroll
       for (int g = 0; g < G; g++) {
-        lpart[g] = warp_sum(lpart[g]);
-        if (lane == 0) red[warp * G + g] = lpart[g];
+        const float ls = warp_sum(epi_bwd.lpart[g]);
+        if (lane == 0) red[warp * G + g] = ls;
       }
       // write this frame's gradient rows (coalesced over pdfs) while the other warps finish
       float gsum[G], ab[G];  // the reference's frame-0 self-check sums (chain-computation.cc:363-371)

@@ -18,6 +18,7 @@
 // thresholded atomicAdd / atomicCAS log-add per arc, chain-kernels.cu:53-87,
 // chain-log-domain-kernels.cu:62-75).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -146,22 +147,25 @@ __device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <bool LOG, int GEN_NT, bool GROWS = false>
+// RS: the graph itself (the three record arrays, both CSR index arrays and the pdf offsets) is copied into shared
+// memory once per CTA: numerator graphs are a few hundred arcs, and every per-frame step is a short dependent chain
+// in which a record load from L1/L2 is the longest link.
+template <bool LOG, int GEN_NT, bool GROWS = false, bool RS = false>
 __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericParams p) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float scratch[64];
   const int S = p.S, D = p.D, T = p.T, K = p.K;
   const int b = blockIdx.x, tid = threadIdx.x;
   const size_t gb = (p.flags & CHAIN_B200_GRAPH_SHARED) ? 0 : (size_t)b;
-  const int32_t *__restrict__ fi = p.fi + gb * S * 2;
-  const int32_t *__restrict__ bi = p.bi + gb * S * 2;
+  const int32_t *fi = p.fi + gb * S * 2;
+  const int32_t *bi = p.bi + gb * S * 2;
   const float *__restrict__ lk = LOG ? nullptr : p.leaky + gb * S;
   const float *__restrict__ ini = p.init + gb * S;
   const float *__restrict__ fin = p.fin + gb * S;
-  const int32_t *__restrict__ pptr = p.pdf_ptr + gb * (D + 1);
-  const uint2 *__restrict__ prec = p.pdf_rec + gb * K;
-  const uint2 *__restrict__ brec = p.bwd_rec + gb * K;
-  const uint2 *__restrict__ frec = p.fwd_rec + gb * K;
+  const int32_t *pptr = p.pdf_ptr + gb * (D + 1);
+  const uint2 *prec = p.pdf_rec + gb * K;
+  const uint2 *brec = p.bwd_rec + gb * K;
+  const uint2 *frec = p.fwd_rec + gb * K;
   const float *__restrict__ x = p.x + (size_t)b * T * D;
   float *__restrict__ grad = p.grad + (size_t)b * T * D;
   float *__restrict__ alpha_ws = p.alpha_ws + (size_t)b * (T + 1) * S;
@@ -178,6 +182,18 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
   constexpr bool PF = LOG && !GROWS;
   float *bufD = rows + 3 * S;
   float *xb[2] = {rows + 4 * S, rows + 4 * S + D};
+  if constexpr (RS) {  // graph -> shared memory (after the state rows and frames), 8-byte aligned
+    const size_t fl = LOG ? (size_t)4 * S + 2 * D : (size_t)3 * S + D;
+    uint2 *r_s = reinterpret_cast<uint2 *>(smem + ((fl + 1) & ~(size_t)1));
+    int32_t *i_s = reinterpret_cast<int32_t *>(r_s + (size_t)3 * K);
+    for (int k = tid; k < K; k += GEN_NT) { r_s[k] = brec[k]; r_s[K + k] = frec[k]; r_s[2 * K + k] = prec[k]; }
+    for (int i = tid; i < 2 * S; i += GEN_NT) { i_s[i] = bi[i]; i_s[2 * S + i] = fi[i]; }
+    for (int n = tid; n <= D; n += GEN_NT) i_s[4 * S + n] = pptr[n];
+    brec = r_s; frec = r_s + K; prec = r_s + 2 * K;
+    bi = i_s; fi = i_s + 2 * S; pptr = i_s + 4 * S;
+    __syncthreads();
+  }
+  auto REC = [&](const uint2 *q) { return RS ? *q : __ldg(q); };
   const bool clamp_use = PF && (p.flags & CHAIN_B200_CLAMP_X);
   auto XV = [&](int n) { return clamp_use ? clampf(x_s[n], kClampLo, kClampHi) : x_s[n]; };
   auto issue_frame = [&](int f, const float *arow, float *adst) {  // x frame f (+ optionally one alpha row)
@@ -232,7 +248,7 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
         float acc = 0.f;
         const int k1 = bi[2 * h + 1];
         for (int k = bi[2 * h]; k < k1; k++) {
-          const uint2 r = __ldg(&brec[k]);
+          const uint2 r = REC(&brec[k]);
           acc += bufA[r.x & 0xffffu] * __uint_as_float(r.y) * x_s[r.x >> 16];
         }
         const float a = acc * inv;
@@ -255,7 +271,7 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
         const int k0 = bi[2 * h], k1 = bi[2 * h + 1];
         float m = -INFINITY, sm = 0.f;
         for (int k = k0; k < k1; k++) {
-          const uint2 r = __ldg(&brec[k]);
+          const uint2 r = REC(&brec[k]);
           lse_add(m, sm, bufA[r.x & 0xffffu] + __uint_as_float(r.y) + XV(r.x >> 16));
         }
         const float a = (m > -INFINITY) ? m + logf(sm) - tot_prev : -INFINITY;
@@ -324,7 +340,7 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
         float g = 0.f;
         const int j1 = pptr[n + 1];
         for (int j = pptr[n]; j < j1; j++) {
-          const uint2 r = prec[j];
+          const uint2 r = REC(&prec[j]);
           g += bufA[r.x & 0xffffu] * __uint_as_float(r.y) * bufB[r.x >> 16];
         }
         const float gam = g * x_s[n] * inv;
@@ -337,7 +353,7 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
         float acc = 0.f;
         const int k1 = fi[2 * h + 1];
         for (int k = fi[2 * h]; k < k1; k++) {
-          const uint2 r = __ldg(&frec[k]);
+          const uint2 r = REC(&frec[k]);
           acc += __uint_as_float(r.y) * bufB[r.x & 0xffffu] * x_s[r.x >> 16];
         }
         const float bd = acc * inv;
@@ -360,7 +376,7 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
         const float xn = XV(n) - tot_t;
         float m = -INFINITY, sm = 0.f;
         for (int j = j0; j < j1; j++) {
-          const uint2 r = __ldg(&prec[j]);
+          const uint2 r = REC(&prec[j]);
           lse_add(m, sm, bufA[r.x & 0xffffu] + __uint_as_float(r.y) + bufB[r.x >> 16] + xn);
         }
         float lg = -INFINITY, gam = 0.f;
@@ -375,7 +391,7 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
         const int k0 = fi[2 * h], k1 = fi[2 * h + 1];
         float m = -INFINITY, sm = 0.f;
         for (int k = k0; k < k1; k++) {
-          const uint2 r = __ldg(&frec[k]);
+          const uint2 r = REC(&frec[k]);
           lse_add(m, sm, __uint_as_float(r.y) + bufB[r.x & 0xffffu] + XV(r.x >> 16) - tot_t);
         }
         const float v = (m > -INFINITY) ? m + logf(sm) : -INFINITY;
@@ -570,15 +586,20 @@ static int run_generic(const int32_t *ft, const int32_t *fi, const float *fp, co
   p.rows_ws = (float *)(base + w.rows);
 
   const int nt = grows ? 1024 : ((S <= 160) ? 128 : (S <= 448 ? 256 : 1024));
+  // small graphs (numerators): the records and CSR arrays live in shared memory too
+  const size_t rs_extra = 8 + sizeof(uint2) * 3 * (size_t)K + sizeof(int32_t) * ((size_t)4 * S + D + 1);
+  const bool rs = !grows && nt <= 256 && K > 0 && smem + rs_extra <= 96 * 1024 && !getenv("CHAIN_B200_NO_RS");
+  size_t smem_launch = smem + (rs ? rs_extra : 0);
   void (*kern)(const GenericParams) = chain_generic_kernel<LOG, 256>;
   if (nt == 128) kern = chain_generic_kernel<LOG, 128>;
   if (nt == 1024) kern = chain_generic_kernel<LOG, 1024>;
   if (grows) kern = chain_generic_kernel<LOG, 1024, true>;
-  if (smem > 48 * 1024) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (rs) kern = (nt == 128) ? chain_generic_kernel<LOG, 128, false, true> : chain_generic_kernel<LOG, 256, false, true>;
+  if (smem_launch > 48 * 1024) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch);
     if (e != cudaSuccess) return (int)e;
   }
-  kern<<<B, nt, smem, stream>>>(p);
+  kern<<<B, nt, smem_launch, stream>>>(p);
   g_launch_count++;
   launch_finalize(p.logp, p.diag, p.lengths, B, T, LOG ? 0 : 1, objf, ok, diag, stream);
   g_launch_count++;

@@ -69,7 +69,30 @@ def _ok_host(ok_dev):
     return buf
 
 
-def _report(r, batch, log_domain):
+def _per_frame_check(r, lengths, log_domain):
+    """The reference re-runs its self-check on EVERY frame at verbose level >= 1 (chain-computation.cc:337,
+    chain-log-domain-computation.cc:276-279): sum_n gamma(t,n) over the sequences alive at t must equal their number.
+    Recomputed here from the gradient the kernels wrote (a debugging aid: it synchronises, like the reference's).
+    Returns False when a frame is off by more than 5 %."""
+    import sys
+    g = r.grad.exp() if log_domain else r.grad
+    rows = g.sum(-1)                                              # [B,T]
+    T = rows.size(1)
+    alive = (torch.arange(T, device=rows.device)[None, :] < lengths.to(rows.device)[:, None])
+    sums = (rows * alive).sum(0).tolist()
+    counts = alive.sum(0).tolist()
+    ok = True
+    for t in range(T - 1, 0, -1):                                 # frame 0 is reported by the caller
+        s, n = sums[t], float(counts[t])
+        if n and not abs(s - n) < s * 0.01:                       # ApproxEqual(s, n, 0.01), base.cc:6-10
+            print("On time {}, log-prob-deriv sum {} != {}".format(t, s, n), file=sys.stderr)
+            if abs(s - n) > 0.05 * n or s != s:
+                print("Excessive error detected, will abandon this minibatch", file=sys.stderr)
+                ok = False
+    return ok
+
+
+def _report(r, batch, log_domain, lengths=None):
     """`ok` for the caller + what the reference's self-check prints to stderr
     (chain-computation.cc:363-390, chain-log-domain-computation.cc:289-303) from the device-side
     diagnostics.  Quiet level: no synchronisation.  Verbose level >= 1: synchronise, report always
@@ -80,6 +103,8 @@ def _report(r, batch, log_domain):
     if not verbose:
         return _ok_host(r.ok)
     ok = bool(r.ok.item())
+    if lengths is not None:
+        ok = _per_frame_check(r, lengths, log_domain) and ok
     ab, gs = (float(v) for v in r.diag.tolist())
     if not log_domain:
         print("On time 0, alpha-beta product {} != {}".format(ab, batch), file=sys.stderr)
@@ -106,7 +131,7 @@ def forward_backward(forward_transitions, forward_transition_indices, forward_tr
         _check_contiguous(t, n)
     r = engine.forward_backward_prob(g, exp_nnet_output, sequence_lengths, num_states, leaky_hmm_coefficient,
                                      x_is_exp=True, clamp=False)
-    return [r.objf, r.grad, _report(r, exp_nnet_output.size(0), False)]
+    return [r.objf, r.grad, _report(r, exp_nnet_output.size(0), False, sequence_lengths)]
 
 
 def forward_backward_log_domain(forward_transitions, forward_transition_indices, forward_transition_probs,
@@ -119,7 +144,7 @@ def forward_backward_log_domain(forward_transitions, forward_transition_indices,
     for t, n in zip(g, engine._GRAPH_NAMES_LOG):
         _check_contiguous(t, n)
     r = engine.forward_backward_log(g, nnet_output, sequence_lengths, num_states, grad_as_log=True, clamp=False)
-    return [r.objf, r.grad, _report(r, nnet_output.size(0), True)]
+    return [r.objf, r.grad, _report(r, nnet_output.size(0), True, sequence_lengths)]
 
 
 def set_verbose_level(level):

@@ -136,6 +136,16 @@ def test_ok_flag_and_verbose_report(cuda, capfd):
         assert bool(ok.item()) and "alpha-beta product" in err and "log-prob-deriv sum" in err
     finally:
         new_C.set_verbose_level(0)
+    # verbose level: EVERY frame is re-checked (chain-computation.cc:337); a frame with NaN input is named
+    new_C.set_verbose_level(1)
+    try:
+        bad_mid = x.clone()
+        bad_mid[1, 4, :] = float("nan")
+        objf, grad, ok = new_C.forward_backward(*args(bad_mid))
+        err = capfd.readouterr().err
+        assert not bool(ok.item()) and "On time 4, log-prob-deriv sum" in err
+    finally:
+        new_C.set_verbose_level(0)
     bad = x.clone()
     bad[1, 2, :] = float("nan")
     objf, grad, ok = new_C.forward_backward(*args(bad))

@@ -50,7 +50,8 @@ def test_no_aten_elementwise_between_our_kernels(cuda):
     assert engine.launch_count() - n0 == 7
     names = [e.key for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA]
     kernels = [n for n in names if "memcpy" not in n.lower() and "memset" not in n.lower()]
-    foreign = [n for n in kernels if "chainb200" not in n]
+    # the one launch that is not ours is autograd's own seed: `loss.backward()` fills a 1-element ones tensor
+    foreign = [n for n in kernels if "chainb200" not in n and "FillFunctor" not in n]
     assert not foreign, foreign
 
 
