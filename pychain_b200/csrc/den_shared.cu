@@ -108,15 +108,16 @@ __device__ __forceinline__ void consume_rec1(const uint32_t ab, const float w, c
 // sum_k w_k * A[a_k][g] * Bv[b_k][g] over the row's records (ONE: sum_k w_k * A[a_k][g]).  The warp's slots are one
 // contiguous stream consumed in pairs by a flat counted loop; two register banks of NF pairs alternate: while one
 // bank is consumed the other is being filled, so NF pairs of 128-bit record loads are always in flight per lane.
+// The epilogue is a small functor passed and returned BY VALUE (its accumulators stay in registers).
 //
-// The pass is a real function (__noinline__): the kernel around it keeps some forty values alive across a pass
-// (pointers, sizes, loop state), and inlined they compete with the record banks for the 128 registers a 512-thread
-// CTA allows -- ptxas then spills bank entries right after their loads, which serialises the warp on the L2 latency
-// of the record stream, the very thing the banks exist to hide.  As a callee the loop has the register file to itself
-// (the caller's state is saved once per pass) and the banks can be as deep as the latency asks.
-// The epilogue is a small functor passed and returned BY VALUE (its accumulators live in the callee's registers).
+// Bank depth is what the 128 registers of a 512-thread CTA allow: measured on B200 (cfg4, ms per call, uniform /
+// biphone graph): banks of 3 (two-operand) and 5 (one-operand) pairs 8.00 / 5.84-5.91; banks of 4 and 5: 8.11-8.54 /
+// 6.14-6.18 (ptxas then spills bank entries right after their loads, which serialises the warp on the L2 latency the
+// banks exist to hide); 12 warps x banks of 6/8: 10.6 / 7.5; 8 warps x banks of 8/10: 9.9 / 7.6.  Compiling the pass
+// as a real function (CHAIN_B200_INLINE_PASS=0: the loop gets the register file to itself, the caller's state is
+// saved once per pass) measures the same as inlining it (8.00 / 5.84), with or without the pair fence below.
 #ifndef CHAIN_B200_INLINE_PASS
-#define CHAIN_B200_INLINE_PASS 0
+#define CHAIN_B200_INLINE_PASS 1
 #endif
 #if CHAIN_B200_INLINE_PASS
 #define CHAIN_B200_PASS_ATTR __forceinline__

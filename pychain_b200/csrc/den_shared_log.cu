@@ -40,9 +40,8 @@ __device__ __forceinline__ void lse_rec(const uint32_t ab, const float w, const 
 // the index word.
 template <int G, bool L1C, class Epi>
 __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__restrict__ A,
-                                              const float *__restrict__ Bv, uint32_t amax, uint32_t bmax,
-                                              float *__restrict__ partial, int warp, int lane, Epi &epi) {
-  const uint32_t A_s = smem_u32(A), B_s = smem_u32(Bv);
+                                              const float *__restrict__ Bv, float *__restrict__ partial, int warp,
+                                              int lane, Epi &epi) {
   const uint4 *sp = reinterpret_cast<const uint4 *>(v.recs + v.warp_info[3 * warp]) + lane;  // [pair][lane]: 2 records
   const int npairs = (int)v.warp_info[3 * warp + 1];
   uint4 fa[kFifoPairs], fb[kFifoPairs];
@@ -54,15 +53,7 @@ __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__res
   for (int g = 0; g < G; g++) { m[g] = -INFINITY; s[g] = 0.f; }
   // a pair is two arcs, or -- at the end of a slice -- an arc and the lane's row-code slot (weight word = kCodeMarkLog)
   auto process = [&](const uint2 r0, const uint2 r1) {
-    // the operands of both slots are gathered before the flag is looked at (a row-code slot's index fields are
-    // clamped into the rows and what they fetch is dropped)
-    float a0[G], b0[G], a1[G], b1[G];
-    lds_vec<G>(A_s + (r0.x & 0xffffu) * (G * 4u), a0);
-    lds_vec<G>(B_s + (r0.x >> 16) * (G * 4u), b0);
-    lds_vec<G>(A_s + min(r1.x & 0xffffu, amax) * (G * 4u), a1);
-    lds_vec<G>(B_s + min(r1.x >> 16, bmax) * (G * 4u), b1);
-#pragma unroll
-    for (int g = 0; g < G; g++) lse_add_fast(m[g], s[g], a0[g] + __uint_as_float(r0.y) + b0[g]);
+    lse_rec<G>(r0.x, __uint_as_float(r0.y), A, Bv, m, s);
     if (r1.y == kCodeMarkLog) {  // warp-uniform: end of the slice
       const int row = (int)r1.x;
       if (row >= 0) {
@@ -77,8 +68,7 @@ __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__res
 #pragma unroll
       for (int g = 0; g < G; g++) { m[g] = -INFINITY; s[g] = 0.f; }
     } else {
-#pragma unroll
-      for (int g = 0; g < G; g++) lse_add_fast(m[g], s[g], a1[g] + __uint_as_float(r1.y) + b1[g]);
+      lse_rec<G>(r1.x, __uint_as_float(r1.y), A, Bv, m, s);
     }
   };
   int j = 0;
@@ -294,7 +284,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
         }
         st_vec<G>(Bn + (size_t)row * G, a);
       };
-      sell_pass_log<G, L1C>(p.view[0], A, x_s, S_pad - 1, D_pad - 1, partial, warp, lane, epi_fwd);
+      sell_pass_log<G, L1C>(p.view[0], A, x_s, partial, warp, lane, epi_fwd);
       if (p.view[0].n_split) { __syncthreads(); fixup_split_log<G>(p.view[0], partial, epi_fwd); }
       float nsc[G];
       block_lse_vec<G>(pm, ps, nsc, red);  // contains the barrier that publishes alpha(t)
@@ -367,7 +357,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
         }
         st_vec<G>(gam_s + (size_t)row * G, out);
       };
-      sell_pass_log<G, L1C>(p.view[2], P, Q, S_pad - 1, S_pad - 1, partial, warp, lane, epi_gam);
+      sell_pass_log<G, L1C>(p.view[2], P, Q, partial, warp, lane, epi_gam);
       if (p.view[2].n_split) { __syncthreads(); fixup_split_log<G>(p.view[2], partial, epi_gam); }
       __syncthreads();  // gamma rows complete; everybody done reading P
 
@@ -377,7 +367,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
         for (int g = 0; g < G; g++) out[g] = (o[g] > -INFINITY && t < Lg[g]) ? o[g] - sct[g] : -INFINITY;
         st_vec<G>(P + (size_t)row * G, out);
       };
-      sell_pass_log<G, L1C>(p.view[1], Q, x_s, S_pad - 1, D_pad - 1, partial, warp, lane, epi_bwd);
+      sell_pass_log<G, L1C>(p.view[1], Q, x_s, partial, warp, lane, epi_bwd);
       if (p.view[1].n_split) { __syncthreads(); fixup_split_log<G>(p.view[1], partial, epi_bwd); }
       {  // this frame's gradient rows: one vector read per pdf, G coalesced row writes
         const float dead = as_log ? -INFINITY : 0.f;

@@ -147,25 +147,22 @@ __device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// RS: the graph itself (the three record arrays, both CSR index arrays and the pdf offsets) is copied into shared
-// memory once per CTA: numerator graphs are a few hundred arcs, and every per-frame step is a short dependent chain
-// in which a record load from L1/L2 is the longest link.
-template <bool LOG, int GEN_NT, bool GROWS = false, bool RS = false>
+template <bool LOG, int GEN_NT, bool GROWS = false>
 __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericParams p) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float scratch[64];
   const int S = p.S, D = p.D, T = p.T, K = p.K;
   const int b = blockIdx.x, tid = threadIdx.x;
   const size_t gb = (p.flags & CHAIN_B200_GRAPH_SHARED) ? 0 : (size_t)b;
-  const int32_t *fi = p.fi + gb * S * 2;
-  const int32_t *bi = p.bi + gb * S * 2;
+  const int32_t *__restrict__ fi = p.fi + gb * S * 2;
+  const int32_t *__restrict__ bi = p.bi + gb * S * 2;
   const float *__restrict__ lk = LOG ? nullptr : p.leaky + gb * S;
   const float *__restrict__ ini = p.init + gb * S;
   const float *__restrict__ fin = p.fin + gb * S;
-  const int32_t *pptr = p.pdf_ptr + gb * (D + 1);
-  const uint2 *prec = p.pdf_rec + gb * K;
-  const uint2 *brec = p.bwd_rec + gb * K;
-  const uint2 *frec = p.fwd_rec + gb * K;
+  const int32_t *__restrict__ pptr = p.pdf_ptr + gb * (D + 1);
+  const uint2 *__restrict__ prec = p.pdf_rec + gb * K;
+  const uint2 *__restrict__ brec = p.bwd_rec + gb * K;
+  const uint2 *__restrict__ frec = p.fwd_rec + gb * K;
   const float *__restrict__ x = p.x + (size_t)b * T * D;
   float *__restrict__ grad = p.grad + (size_t)b * T * D;
   float *__restrict__ alpha_ws = p.alpha_ws + (size_t)b * (T + 1) * S;
@@ -182,18 +179,7 @@ __global__ void __launch_bounds__(GEN_NT) chain_generic_kernel(const GenericPara
   constexpr bool PF = LOG && !GROWS;
   float *bufD = rows + 3 * S;
   float *xb[2] = {rows + 4 * S, rows + 4 * S + D};
-  if constexpr (RS) {  // graph -> shared memory (after the state rows and frames), 8-byte aligned
-    const size_t fl = LOG ? (size_t)4 * S + 2 * D : (size_t)3 * S + D;
-    uint2 *r_s = reinterpret_cast<uint2 *>(smem + ((fl + 1) & ~(size_t)1));
-    int32_t *i_s = reinterpret_cast<int32_t *>(r_s + (size_t)3 * K);
-    for (int k = tid; k < K; k += GEN_NT) { r_s[k] = brec[k]; r_s[K + k] = frec[k]; r_s[2 * K + k] = prec[k]; }
-    for (int i = tid; i < 2 * S; i += GEN_NT) { i_s[i] = bi[i]; i_s[2 * S + i] = fi[i]; }
-    for (int n = tid; n <= D; n += GEN_NT) i_s[4 * S + n] = pptr[n];
-    brec = r_s; frec = r_s + K; prec = r_s + 2 * K;
-    bi = i_s; fi = i_s + 2 * S; pptr = i_s + 4 * S;
-    __syncthreads();
-  }
-  auto REC = [&](const uint2 *q) { return RS ? *q : __ldg(q); };
+  auto REC = [&](const uint2 *q) { return __ldg(q); };
   const bool clamp_use = PF && (p.flags & CHAIN_B200_CLAMP_X);
   auto XV = [&](int n) { return clamp_use ? clampf(x_s[n], kClampLo, kClampHi) : x_s[n]; };
   auto issue_frame = [&](int f, const float *arow, float *adst) {  // x frame f (+ optionally one alpha row)
@@ -586,15 +572,11 @@ static int run_generic(const int32_t *ft, const int32_t *fi, const float *fp, co
   p.rows_ws = (float *)(base + w.rows);
 
   const int nt = grows ? 1024 : ((S <= 160) ? 128 : (S <= 448 ? 256 : 1024));
-  // small graphs (numerators): the records and CSR arrays live in shared memory too
-  const size_t rs_extra = 8 + sizeof(uint2) * 3 * (size_t)K + sizeof(int32_t) * ((size_t)4 * S + D + 1);
-  const bool rs = !grows && nt <= 256 && K > 0 && smem + rs_extra <= 96 * 1024 && !getenv("CHAIN_B200_NO_RS");
-  size_t smem_launch = smem + (rs ? rs_extra : 0);
+  const size_t smem_launch = smem;
   void (*kern)(const GenericParams) = chain_generic_kernel<LOG, 256>;
   if (nt == 128) kern = chain_generic_kernel<LOG, 128>;
   if (nt == 1024) kern = chain_generic_kernel<LOG, 1024>;
   if (grows) kern = chain_generic_kernel<LOG, 1024, true>;
-  if (rs) kern = (nt == 128) ? chain_generic_kernel<LOG, 128, false, true> : chain_generic_kernel<LOG, 256, false, true>;
   if (smem_launch > 48 * 1024) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch);
     if (e != cudaSuccess) return (int)e;
