@@ -42,11 +42,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg4")
-    ap.add_argument("--variant", default="biphone", choices=["uniform", "skew", "biphone"],
+    ap.add_argument("--variant", default=None, choices=["uniform", "skew", "biphone"],
                     help="structure of the synthetic denominator FST.  biphone (default; BASELINE.json names cfg4 'biphone "
                          "denominator'): states = phone pairs, the pdf of an arc is a function of its destination, as in "
                          "chain graphs.  uniform: every arc draws its pdf at random (the worst case: no (dst,pdf) class "
-                         "has two arcs).  skew: uniform pdfs, Zipf in-degrees.  The default run also times the other two.")
+                         "has two arcs).  skew: uniform pdfs, Zipf in-degrees.  Default: biphone for cfg4 (whose run also times "
+                         "the other two), uniform (SURVEY.md 8d) for the other configs.")
     ap.add_argument("--no-other-variants", action="store_true", help="skip the short timing of the other FST variants")
     ap.add_argument("--cpu-sample", type=int, default=0, help="utterances in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -55,7 +56,10 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the config's batch per GPU; strong: the config's GLOBAL batch split over the GPUs")
     ap.add_argument("--probe", action="store_true", help=argparse.SUPPRESS)
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.variant is None:
+        a.variant = "biphone" if a.config == "cfg4" else "uniform"
+    return a
 
 
 # ------------------------------------------------------------------ clocks

@@ -20,6 +20,12 @@
 // Log-domain blobs (header.log_domain = 1; weights are log-probabilities, idle records carry -inf) keep
 // the end-of-slice flag in bit 31 of the index word instead (so S, D <= 32767); their sub-rows hand
 // over (max, sum-exp) pairs instead of plain partial sums.
+// TWO STREAM FORMATS (header.embed_codes).  Large graphs stream their records from L2 every frame, and there the row
+// code of a slice must arrive through the same prefetched stream (a separate load per slice exposes a full L2
+// latency on the thin slices chain graphs are full of): the LAST slot of every lane of a slice is {row code, -aux}
+// (sign bit = "this is the code"; aux = leaky(row) in view 1), at the price of one slot per slice.  Small graphs
+// whose record streams stay in L1 (records_fit_l1) keep the compact format: no code slot, the sign bit of the
+// last arc's weight ends the slice, row codes come from a parallel per-warp stream read two slices ahead.
 // Rows whose degree exceeds the view's cap are split into sub-rows; a sub-row writes its
 // partial sum to a scratch slot and the listed owner adds the slots up in order.
 //
@@ -43,7 +49,7 @@
 namespace chainb200 {
 
 constexpr uint32_t kBlobMagic = 0x42324348u;  // "HC2B"
-constexpr uint32_t kBlobVersion = 12;
+constexpr uint32_t kBlobVersion = 13;
 constexpr uint32_t kCodeMarkLog = 0x7fc0c0deu;  // log-domain blobs: weight word of a row-code slot (a NaN no arc can carry)
 #ifndef CHAIN_B200_NW
 #define CHAIN_B200_NW 16
@@ -73,6 +79,10 @@ struct BlobHeader {
   int32_t S, K, D, nwarps, S_pad, D_pad, max_sub, log_domain;
   int32_t opt_G;               // group width whose bank geometry the column order was optimised for
   int32_t C, C_pad, R_pad;     // selected (dst,pdf) classes; R_pad = S_pad + C_pad = floats per utterance of a state row
+  int32_t embed_codes;         // 1: the last slot of every slice carries the lane's row code (streams read from L2);
+                               // 0: row codes are a separate per-warp stream and the end-of-slice flag sits on the last
+                               //    arc (graphs whose records stay resident in L1 next to the CTA's shared memory)
+  int32_t reserved0;
   BlobView view[kNumViews];
   int64_t off_leaky, off_init, off_final;
   int64_t off_cls_dst, off_cls_pdf;  // int32 [C_pad] destination state / pdf of each class

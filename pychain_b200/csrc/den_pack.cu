@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <numeric>
 #include <vector>
 
@@ -239,7 +240,7 @@ struct ArcSet {
 // row_flags: optional per-row bits OR-ed into the row code (kRowExtraFlag).
 static void build_view(int n_rows, const ArcSet &arcs, int n_a, int n_b, bool structure_only, bool log_domain, int P,
                        bool skip_empty, const std::vector<int32_t> *row_flags, int effort_K, bool one_operand,
-                       const float *row_aux, ViewBuild &v) {
+                       const float *row_aux, bool embed, ViewBuild &v) {
   v.n_rows = n_rows;
   const int K = arcs.size();
   const std::vector<int32_t> &row_of = arcs.row_of;
@@ -311,17 +312,16 @@ static void build_view(int n_rows, const ArcSet &arcs, int n_a, int n_b, bool st
       v.rows[i] = lanes[l]->row_code;
       width = std::max(width, (int)lanes[l]->arcs.size());
     }
-    // the LAST slot of every lane is not an arc: it carries the lane's row code (and one float the epilogue wants,
-    // e.g. leaky(row) for the beta' pass) through the same prefetched stream as the records, so the end of a
-    // slice costs no load of its own -- slices of one or two arcs (chain graphs are full of them) would otherwise
-    // expose a full L2 latency each.  Slots are consumed in pairs: width = arcs + 1, rounded up to even.
-    width = (width + 2) & ~1;
+    // embed: the LAST slot of every lane is not an arc but the lane's row code (see den_blob.h): width = arcs + 1,
+    // rounded up to even (slots are consumed in pairs).  Otherwise width = arcs rounded up to even, >= 2.
+    const int ncode = embed ? 1 : 0;
+    width = embed ? ((width + 2) & ~1) : std::max(2, width + (width & 1));
     std::vector<int> cols;
-    arrange_slice(lanes, width - 1, cols, rng, structure_only ? 0 : effort, P);
+    arrange_slice(lanes, width - ncode, cols, rng, structure_only ? 0 : effort, P);
     v.width[s] = width;
     s_ab[s].assign((size_t)width * 32, 0u);
     s_w[s].assign((size_t)width * 32, log_domain ? -INFINITY : 0.f);
-    for (int l = 0; l < 32; l++) {
+    for (int l = 0; embed && l < 32; l++) {
       const size_t i = (size_t)s * 32 + l;
       const int32_t code = (i < units.size()) ? lanes[l]->row_code : -1;
       float aux = (row_aux && code >= 0) ? fabsf(row_aux[code & 0xfffff]) : 0.f;
@@ -336,7 +336,7 @@ static void build_view(int n_rows, const ArcSet &arcs, int n_a, int n_b, bool st
       s_ab[s][(size_t)(width - 1) * 32 + l] = (uint32_t)code;
       memcpy(&s_w[s][(size_t)(width - 1) * 32 + l], &mark, 4);
     }
-    for (int k = 0; k < width - 1; k++) {
+    for (int k = 0; k < width - ncode; k++) {
       uint32_t ia[32], ib[32];
       for (int l = 0; l < 32; l++) {
         const int j = cols[(size_t)k * 32 + l];
@@ -398,11 +398,13 @@ static void build_view(int n_rows, const ArcSet &arcs, int n_a, int n_b, bool st
   v.warp_info.assign((size_t)DEN_NW * 3, 0);
   v.rec_ab.clear();
   v.rec_w.clear();
+  std::vector<int32_t> rows_seq;
   for (int wv = 0; wv < DEN_NW; wv++) {
     const size_t rec0 = v.rec_ab.size();
     v.warp_info[3 * wv + 0] = (int64_t)rec0;
-    v.warp_info[3 * wv + 2] = (int64_t)per[wv].size();   // slices of this warp (informational)
+    v.warp_info[3 * wv + 2] = embed ? (int64_t)per[wv].size() : (int64_t)rows_seq.size();  // slices / row-code offset
     for (int s : per[wv]) {
+      if (!embed) rows_seq.insert(rows_seq.end(), v.rows.begin() + (size_t)s * 32, v.rows.begin() + (size_t)s * 32 + 32);
       // records are consumed in pairs: the two records of a lane's pair are ADJACENT (16 bytes, one 128-bit
       // load per lane and pair, 512 contiguous bytes per warp): [pair][lane][2]
       const int width = v.width[s];
@@ -412,14 +414,28 @@ static void build_view(int n_rows, const ArcSet &arcs, int n_a, int n_b, bool st
             v.rec_ab.push_back(s_ab[s][(size_t)(2 * j + h) * 32 + l]);
             v.rec_w.push_back(s_w[s][(size_t)(2 * j + h) * 32 + l]);
           }
+      if (!embed) {  // end-of-slice flag on the second slot of every lane's last pair
+        const size_t last = v.rec_w.size() - 64;
+        for (int l = 0; l < 32; l++) {
+          const size_t q = last + 2 * l + 1;
+          if (log_domain) {
+            v.rec_ab[q] |= 0x80000000u;
+          } else {
+            v.rec_w[q] = -fabsf(v.rec_w[q]);
+            if (!std::signbit(v.rec_w[q])) v.rec_w[q] = -0.0f;
+          }
+        }
+      }
     }
+    if (!embed) rows_seq.insert(rows_seq.end(), 3 * 32, -1);  // the row prefetch runs slices ahead
     size_t pairs = (v.rec_ab.size() - rec0) / 64;
     const size_t run = pairs;  // the kernel runs the last (partial) double bank through a predicated tail
     v.warp_info[3 * wv + 1] = (int64_t)run;
     v.rec_ab.insert(v.rec_ab.end(), (size_t)3 * kFifoPairs * 64, 0u);  // register-bank run-out
     v.rec_w.insert(v.rec_w.end(), (size_t)3 * kFifoPairs * 64, log_domain ? -INFINITY : 0.f);
   }
-  v.rows.clear();   // the row codes travel inside the record streams
+  if (embed) v.rows.clear();   // the row codes travel inside the record streams
+  else v.rows.swap(rows_seq);
 }
 
 }  // namespace
@@ -458,6 +474,7 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
   }
   const int S_pad = (S + 3) / 4 * 4, D_pad = (D + 3) / 4 * 4;
   const bool so = (out == nullptr);
+  bool embed = false;   // stream format (den_blob.h), decided below from how thin the slices of views 0 and 1 are
 
   // ---- (dst, pdf) classes: the arcs of one destination that share a pdf (see den_blob.h) ----------------
   // candidates in backward-CSR order (arcs grouped by destination), members keep their CSR order
@@ -541,14 +558,31 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
     }
   }
   for (int c = 0; c < C; c++) a2.push(cls[c].pdf, (uint32_t)(S_pad + c) | ((uint32_t)cls[c].dst << 16), one);
+  // Stream format: a slice of one arc pair or less leaves the separate row-code stream (read two slices ahead) no
+  // time to cover its L2 latency -- chain graphs, whose states keep a self loop and one class arc, are made of such
+  // slices -- so their row codes travel inside the record streams (one extra slot per slice); graphs with fat
+  // slices keep the compact format, where that slot would be pure overhead (measured: cfg5, 5 arcs per state, 1.41 ms
+  // compact vs 1.67 ms embedded; cfg4 biphone 7.2 ms compact vs 6.3 ms embedded).
+  {
+    auto thin_fraction = [&](int n_rows, const ArcSet &as) {
+      std::vector<int> deg(n_rows, 0);
+      for (int r : as.row_of) deg[r]++;
+      std::sort(deg.begin(), deg.end(), std::greater<int>());
+      int thin = 0, n_sl = 0;
+      for (int i = 0; i < n_rows; i += 32, n_sl++) thin += deg[i] <= 2;   // the slice's longest row: <= one pair
+      return n_sl ? (double)thin / n_sl : 0.0;
+    };
+    embed = std::max(thin_fraction(S, a0), thin_fraction(S, a1)) > 0.25;
+    if (const char *e = getenv("CHAIN_B200_EMBED_CODES")) embed = atoi(e) != 0;
+  }
   for (int i = 0; i < kNumViews; i++) vb[i] = ViewBuild();
   // n_a / n_b bound what an IDLE lane may gather (weight 0): only entries that always hold finite data, i.e. the
   // S real states / D real pdfs -- never the row padding or the class extension (0 * garbage = NaN)
-  build_view(S, a0, S, D, so, log_domain, P, false, nullptr, Kv, false, nullptr, vb[0]);
-  build_view(S, a1, S, D, so, log_domain, P, false, C > 0 ? &flags1 : nullptr, Kv, false, log_domain ? nullptr : leaky, vb[1]);
-  build_view(D, a2, S, S, so, log_domain, P, false, nullptr, Kv, false, nullptr, vb[2]);
-  build_view(std::max(C, 1), a3, S, 1, so, log_domain, P, true, nullptr, Kv, true, nullptr, vb[3]);
-  build_view(S, a4, S, 1, so, log_domain, P, true, nullptr, Kv, true, nullptr, vb[4]);
+  build_view(S, a0, S, D, so, log_domain, P, false, nullptr, Kv, false, nullptr, embed, vb[0]);
+  build_view(S, a1, S, D, so, log_domain, P, false, C > 0 ? &flags1 : nullptr, Kv, false, log_domain ? nullptr : leaky, embed, vb[1]);
+  build_view(D, a2, S, S, so, log_domain, P, false, nullptr, Kv, false, nullptr, embed, vb[2]);
+  build_view(std::max(C, 1), a3, S, 1, so, log_domain, P, true, nullptr, Kv, true, nullptr, embed, vb[3]);
+  build_view(S, a4, S, 1, so, log_domain, P, true, nullptr, Kv, true, nullptr, embed, vb[4]);
   // split-row slots share the chip with the class sums: give classes back until everything fits
   int max_sub = 0;
   for (int i = 0; i < kNumViews; i++) max_sub = std::max(max_sub, vb[i].n_sub);
@@ -564,6 +598,7 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
   h.opt_G = 32 / P;
   h.S_pad = S_pad; h.D_pad = D_pad;
   h.C = C; h.C_pad = C_pad; h.R_pad = R_pad;
+  h.embed_codes = embed ? 1 : 0;
   size_t off = align_up(sizeof(BlobHeader));
   for (int i = 0; i < kNumViews; i++) {
     BlobView &bv = h.view[i];

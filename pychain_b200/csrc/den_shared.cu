@@ -124,11 +124,20 @@ __device__ __forceinline__ void consume_rec1(const uint32_t ab, const float w, c
 #else
 #define CHAIN_B200_PASS_ATTR __noinline__
 #endif
-template <int G, bool L1C, bool ONE, int NF, class Epi>
+// EMBED: stream format of the blob (den_blob.h): row codes in the last slot of every slice, or (compact format)
+// a parallel stream `rp` of row codes read two slices ahead, the slice ending on the sign bit of its last arc's
+// weight and the epilogue's per-row float coming from `aux_tab`.
+template <int G, bool L1C, bool EMBED, bool ONE, int NF, class Epi>
 __device__ CHAIN_B200_PASS_ATTR Epi sell_pass(const uint4 *__restrict__ sp, const int npairs, const uint32_t A_s,
                                       const uint32_t B_s, const uint32_t amax, const uint32_t bmax,
-                                      const uint32_t part_s, Epi epi) {
+                                      const uint32_t part_s, const int32_t *__restrict__ rp,
+                                      const float *__restrict__ aux_tab, Epi epi) {
   uint4 fa[NF], fb[NF];
+  int row = 0, row_n1 = 0, row_n2 = 0;
+  if constexpr (!EMBED) {
+    row = __ldg(rp); row_n1 = __ldg(rp + 32); row_n2 = __ldg(rp + 64);
+    rp += 96;
+  }
 #pragma unroll
   for (int d = 0; d < NF; d++) fa[d] = ldg_stream<L1C>(sp + d * 32);
   sp += NF * 32;
@@ -138,34 +147,49 @@ __device__ CHAIN_B200_PASS_ATTR Epi sell_pass(const uint4 *__restrict__ sp, cons
   // A pair is two arcs, or -- at the end of a slice -- an arc and the lane's ROW-CODE slot (sign bit of its second
   // word; warp-uniform): {row code, -aux}.  The code arrives through the same prefetched stream as the arcs.
   // The operands of BOTH slots are gathered before the flag is looked at: a row-code slot is not an arc, so its
-  // index fields are clamped into the rows (amax / bmax) and what they fetch is dropped.
+  // index fields are clamped (amax / bmax) into the part of the rows that real arcs of this view read -- never into
+  // a region another warp may be writing during the pass -- and what they fetch is dropped.
   auto process = [&](const uint2 r0, const uint2 r1) {
+    const bool last = (r1.y & 0x80000000u) != 0;                  // warp-uniform
+    const bool arc1 = !EMBED || !last;                            // compact format: the flagged slot is still an arc
+    const float w1 = __uint_as_float(EMBED ? r1.y : (r1.y & 0x7fffffffu));
     if constexpr (ONE) {
       float a0[G], a1[G];
       lds_vec<G>(A_s + (r0.x & 0xffffu) * (G * 4u), a0);
-      lds_vec<G>(A_s + min(r1.x & 0xffffu, amax) * (G * 4u), a1);
+      lds_vec<G>(A_s + (EMBED ? min(r1.x & 0xffffu, amax) : (r1.x & 0xffffu)) * (G * 4u), a1);
       fma_rec1<G>(acc, a0, __uint_as_float(r0.y));
-      if (!(r1.y & 0x80000000u)) fma_rec1<G>(acc, a1, __uint_as_float(r1.y));
+      if (arc1) fma_rec1<G>(acc, a1, w1);
     } else {
       float a0[G], a1[G], b0[G], b1[G];
       lds_vec<G>(A_s + (r0.x & 0xffffu) * (G * 4u), a0);
-      lds_vec<G>(A_s + min(r1.x & 0xffffu, amax) * (G * 4u), a1);
+      lds_vec<G>(A_s + (EMBED ? min(r1.x & 0xffffu, amax) : (r1.x & 0xffffu)) * (G * 4u), a1);
       lds_vec<G>(B_s + (r0.x >> 16) * (G * 4u), b0);
-      lds_vec<G>(B_s + min(r1.x >> 16, bmax) * (G * 4u), b1);
+      lds_vec<G>(B_s + (EMBED ? min(r1.x >> 16, bmax) : (r1.x >> 16)) * (G * 4u), b1);
       fma_rec<G>(acc, a0, __uint_as_float(r0.y), b0);
-      if (!(r1.y & 0x80000000u)) fma_rec<G>(acc, a1, __uint_as_float(r1.y), b1);
+      if (arc1) fma_rec<G>(acc, a1, w1, b1);
     }
-    if (r1.y & 0x80000000u) {
-      const int row = (int)r1.x;
-      if (row >= 0) epi(row, acc, __uint_as_float(r1.y & 0x7fffffffu));
-      else if (row <= -2) sts_vec<G>(part_s + (uint32_t)(-2 - row) * (G * 4u), acc);
+    if (last) {
+      if constexpr (EMBED) row = (int)r1.x;
+      if (row >= 0) {
+        float aux = 0.f;
+        if constexpr (EMBED) aux = __uint_as_float(r1.y & 0x7fffffffu);
+        else if (aux_tab) aux = __ldg(aux_tab + (row & (kRowExtraFlag - 1)));
+        epi(row, acc, aux);
+      } else if (row <= -2) {
+        sts_vec<G>(part_s + (uint32_t)(-2 - row) * (G * 4u), acc);
+      }
 #pragma unroll
       for (int g = 0; g < G; g++) acc[g] = 0.f;
+      if constexpr (!EMBED) {
+        row = row_n1;
+        row_n1 = row_n2;
+        row_n2 = __ldg(rp);
+        rp += 32;
+      }
     }
     if constexpr (kPairFence) {
       // keep the gathers of the next pair behind this pair's arithmetic: the operand registers of ONE pair are live at
-      // a time, the rest of the register file holds record banks (the LDS latency this exposes is covered by the other
-      // 15 warps; the L2 latency of the record stream is not)
+      // a time, the rest of the register file holds record banks
 #pragma unroll
       for (int g = 0; g < G; g++) asm volatile("" : "+f"(acc[g]));
     }
@@ -202,11 +226,13 @@ __device__ CHAIN_B200_PASS_ATTR Epi sell_pass(const uint4 *__restrict__ sp, cons
 }
 
 // Launch one pass for this warp: stream start / length of view `v`.
-template <int G, bool L1C, bool ONE, int NF, class Epi>
+template <int G, bool L1C, bool EMBED, bool ONE, int NF, class Epi>
 __device__ __forceinline__ Epi run_pass(const DView &v, uint32_t A_s, uint32_t B_s, uint32_t amax, uint32_t bmax,
-                                        uint32_t part_s, int warp, int lane, Epi epi) {
+                                        uint32_t part_s, const float *aux_tab, int warp, int lane, Epi epi) {
   const uint4 *sp = reinterpret_cast<const uint4 *>(v.recs + v.warp_info[3 * warp]) + lane;  // [pair][lane]: 2 slots
-  return sell_pass<G, L1C, ONE, NF, Epi>(sp, (int)v.warp_info[3 * warp + 1], A_s, B_s, amax, bmax, part_s, epi);
+  const int32_t *rp = EMBED ? nullptr : v.rows + v.warp_info[3 * warp + 2] + lane;
+  return sell_pass<G, L1C, EMBED, ONE, NF, Epi>(sp, (int)v.warp_info[3 * warp + 1], A_s, B_s, amax, bmax, part_s, rp,
+                                                aux_tab, epi);
 }
 
 // ---- the epilogues of the five passes: what happens to a finished row --------------------------------------
@@ -283,7 +309,7 @@ __device__ __forceinline__ void fixup_split(const DView &v, const float *__restr
 // L1C: the three record streams fit in the L1 next to this CTA's shared memory, so they are
 // loaded with L1 allocation and hit L1 from the second frame on (small graphs are latency bound);
 // otherwise they are streamed from L2 without polluting L1.
-template <int G, bool L1C>
+template <int G, bool L1C, bool EMBED>
 __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar[2];  // 0: alpha rows, 1: x frames
@@ -431,7 +457,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         // class sums A_c(t-1) = sum_{arcs of class c} alpha'(t-1,src) * w: one operand per arc.  They extend the
         // state row (virtual states S_pad + c) and are spilled with it: the backward pass needs them again.
         EpiClass<G> epi_cls{smem_u32(A + (size_t)S_pad * G), aws + ((size_t)(t - 1) * R_pad + S_pad) * G};
-        epi_cls = run_pass<G, L1C, true, nf1<G>()>(views[3], smem_u32(A), 0u, R_pad - 1, 0, part_sa, warp, lane, epi_cls);
+        epi_cls = run_pass<G, L1C, EMBED, true, nf1<G>()>(views[3], smem_u32(A), 0u, S - 1, 0, part_sa, nullptr, warp, lane, epi_cls);
         if (p.view[3].n_split) { __syncthreads(); fixup_split<G>(p.view[3], partial, nullptr, epi_cls); }
       }
       __syncthreads();  // x_s complete, xraw free, class sums complete
@@ -440,8 +466,8 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       epi_fwd.out_s = smem_u32(Bn);
 #pragma unroll
       for (int g = 0; g < G; g++) epi_fwd.part[g] = 0.f;
-      epi_fwd = run_pass<G, L1C, false, nf2a<G>()>(views[0], smem_u32(A), smem_u32(x_s), R_pad - 1, D_pad - 1, part_sa,
-                                                   warp, lane, epi_fwd);
+      epi_fwd = run_pass<G, L1C, EMBED, false, nf2a<G>()>(views[0], smem_u32(A), smem_u32(x_s), R_pad - 1, D - 1,
+                                                          part_sa, nullptr, warp, lane, epi_fwd);
       if (p.view[0].n_split) { __syncthreads(); fixup_split<G>(p.view[0], partial, nullptr, epi_fwd); }
 #pragma unroll
       for (int g = 0; g < G; g++) {
@@ -560,15 +586,15 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
 
       // ---- gamma pass: rows = pdfs; gamma(t,n) = x(t,n)/tot(t) * sum alpha'(src) p beta(dst)
       EpiGamma<G> epi_gam{smem_u32(x_s), smem_u32(gam_s)};
-      epi_gam = run_pass<G, L1C, false, nf2<G>()>(views[2], smem_u32(P), smem_u32(Q), R_pad - 1, R_pad - 1, part_sa,
-                                                   warp, lane, epi_gam);
+      epi_gam = run_pass<G, L1C, EMBED, false, nf2<G>()>(views[2], smem_u32(P), smem_u32(Q), R_pad - 1, S - 1,
+                                                          part_sa, nullptr, warp, lane, epi_gam);
       if (p.view[2].n_split) { __syncthreads(); fixup_split<G>(p.view[2], partial, nullptr, epi_gam); }
       __syncthreads();  // gamma rows complete; everybody done reading P; bx complete
 
       // ---- beta' pass, class arcs: rows = source states, one operand (bx_c) per arc; the raw sums wait in P
       if (C) {
         EpiStore<G> epi_b2{smem_u32(P)};
-        epi_b2 = run_pass<G, L1C, true, nf1<G>()>(views[4], smem_u32(Q), 0u, R_pad - 1, 0, part_sa, warp, lane, epi_b2);
+        epi_b2 = run_pass<G, L1C, EMBED, true, nf1<G>()>(views[4], smem_u32(Q), 0u, R_pad - 1, 0, part_sa, nullptr, warp, lane, epi_b2);
         if (p.view[4].n_split) { __syncthreads(); fixup_split<G>(p.view[4], partial, nullptr, epi_b2); }
         __syncthreads();
       }
@@ -578,8 +604,8 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       epi_bwd.out_s = smem_u32(P);
 #pragma unroll
       for (int g = 0; g < G; g++) epi_bwd.lpart[g] = 0.f;
-      epi_bwd = run_pass<G, L1C, false, nf2<G>()>(views[1], smem_u32(Q), smem_u32(x_s), R_pad - 1, D_pad - 1, part_sa,
-                                                   warp, lane, epi_bwd);
+      epi_bwd = run_pass<G, L1C, EMBED, false, nf2<G>()>(views[1], smem_u32(Q), smem_u32(x_s), S - 1, D - 1,
+                                                          part_sa, lk, warp, lane, epi_bwd);
       if (p.view[1].n_split) { __syncthreads(); fixup_split<G>(p.view[1], partial, lk, epi_bwd); }
 #pragma unroll
       for (int g = 0; g < G; g++) {
@@ -733,21 +759,22 @@ int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev,
     g_launch_count++;
     return (int)cudaGetLastError();
   }
-#define LAUNCH_DEN(GG, LL)                                                                                          \
-  do {                                                                                                              \
-    e = cudaFuncSetAttribute(den_shared_kernel<GG, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    if (e != cudaSuccess) return (int)e;                                                                            \
-    den_shared_kernel<GG, LL><<<grid, DEN_NT, smem, stream>>>(p);                                                   \
+#define LAUNCH_DEN(GG, LL, EE)                                                                                         \
+  do {                                                                                                                \
+    e = cudaFuncSetAttribute(den_shared_kernel<GG, LL, EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return (int)e;                                                                              \
+    den_shared_kernel<GG, LL, EE><<<grid, DEN_NT, smem, stream>>>(p);                                                 \
   } while (0)
-  if (l1c) {
-    if (G == 4) LAUNCH_DEN(4, true);
-    else if (G == 2) LAUNCH_DEN(2, true);
-    else LAUNCH_DEN(1, true);
-  } else {
-    if (G == 4) LAUNCH_DEN(4, false);
-    else if (G == 2) LAUNCH_DEN(2, false);
-    else LAUNCH_DEN(1, false);
-  }
+#define LAUNCH_DEN_G(GG)                                       \
+  do {                                                         \
+    if (h.embed_codes) LAUNCH_DEN(GG, false, true);            \
+    else if (l1c) LAUNCH_DEN(GG, true, false);                 \
+    else LAUNCH_DEN(GG, false, false);                         \
+  } while (0)
+  if (G == 4) LAUNCH_DEN_G(4);
+  else if (G == 2) LAUNCH_DEN_G(2);
+  else LAUNCH_DEN_G(1);
+#undef LAUNCH_DEN_G
 #undef LAUNCH_DEN
   g_launch_count++;
   launch_finalize(p.logp, p.diag, lengths, B, T, 1, objf, ok, diag, stream);

@@ -38,12 +38,20 @@ __device__ __forceinline__ void lse_rec(const uint32_t ab, const float w, const 
 // row's records into a running (max, sum-exp) per utterance.  Record streams and the
 // two-bank register prefetch are those of den_shared.cu; the end-of-slice flag is bit 31 of
 // the index word.
-template <int G, bool L1C, class Epi>
+// EMBED: stream format (den_blob.h).  Embedded: the slice ends on a row-code slot (weight word = kCodeMarkLog).  Compact:
+// bit 31 of the second slot's index word ends the slice, row codes come from the parallel stream v.rows.
+template <int G, bool L1C, bool EMBED, class Epi>
 __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__restrict__ A,
                                               const float *__restrict__ Bv, float *__restrict__ partial, int warp,
                                               int lane, Epi &epi) {
   const uint4 *sp = reinterpret_cast<const uint4 *>(v.recs + v.warp_info[3 * warp]) + lane;  // [pair][lane]: 2 records
   const int npairs = (int)v.warp_info[3 * warp + 1];
+  const int32_t *rp = EMBED ? nullptr : v.rows + v.warp_info[3 * warp + 2] + lane;
+  int row_c = 0, row_n1 = 0, row_n2 = 0;
+  if constexpr (!EMBED) {
+    row_c = __ldg(rp); row_n1 = __ldg(rp + 32); row_n2 = __ldg(rp + 64);
+    rp += 96;
+  }
   uint4 fa[kFifoPairs], fb[kFifoPairs];
 #pragma unroll
   for (int d = 0; d < kFifoPairs; d++) fa[d] = ldg_stream<L1C>(sp + d * 32);
@@ -54,8 +62,10 @@ __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__res
   // a pair is two arcs, or -- at the end of a slice -- an arc and the lane's row-code slot (weight word = kCodeMarkLog)
   auto process = [&](const uint2 r0, const uint2 r1) {
     lse_rec<G>(r0.x, __uint_as_float(r0.y), A, Bv, m, s);
-    if (r1.y == kCodeMarkLog) {  // warp-uniform: end of the slice
-      const int row = (int)r1.x;
+    const bool last = EMBED ? (r1.y == kCodeMarkLog) : ((r1.x & 0x80000000u) != 0);  // warp-uniform: end of the slice
+    if (!EMBED) lse_rec<G>(r1.x & 0x7fffffffu, __uint_as_float(r1.y), A, Bv, m, s);
+    if (last) {
+      const int row = EMBED ? (int)r1.x : row_c;
       if (row >= 0) {
         float o[G];
 #pragma unroll
@@ -67,7 +77,13 @@ __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__res
       }
 #pragma unroll
       for (int g = 0; g < G; g++) { m[g] = -INFINITY; s[g] = 0.f; }
-    } else {
+      if constexpr (!EMBED) {
+        row_c = row_n1;
+        row_n1 = row_n2;
+        row_n2 = __ldg(rp);
+        rp += 32;
+      }
+    } else if (EMBED) {
       lse_rec<G>(r1.x, __uint_as_float(r1.y), A, Bv, m, s);
     }
   };
@@ -146,7 +162,7 @@ __device__ __forceinline__ void block_lse_vec(float (&m)[G], float (&s)[G], floa
   __syncthreads();
 }
 
-template <int G, bool L1C>
+template <int G, bool L1C, bool EMBED>
 __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar[2];  // 0: alpha rows, 1: x frames
@@ -284,7 +300,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
         }
         st_vec<G>(Bn + (size_t)row * G, a);
       };
-      sell_pass_log<G, L1C>(p.view[0], A, x_s, partial, warp, lane, epi_fwd);
+      sell_pass_log<G, L1C, EMBED>(p.view[0], A, x_s, partial, warp, lane, epi_fwd);
       if (p.view[0].n_split) { __syncthreads(); fixup_split_log<G>(p.view[0], partial, epi_fwd); }
       float nsc[G];
       block_lse_vec<G>(pm, ps, nsc, red);  // contains the barrier that publishes alpha(t)
@@ -357,7 +373,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
         }
         st_vec<G>(gam_s + (size_t)row * G, out);
       };
-      sell_pass_log<G, L1C>(p.view[2], P, Q, partial, warp, lane, epi_gam);
+      sell_pass_log<G, L1C, EMBED>(p.view[2], P, Q, partial, warp, lane, epi_gam);
       if (p.view[2].n_split) { __syncthreads(); fixup_split_log<G>(p.view[2], partial, epi_gam); }
       __syncthreads();  // gamma rows complete; everybody done reading P
 
@@ -367,7 +383,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
         for (int g = 0; g < G; g++) out[g] = (o[g] > -INFINITY && t < Lg[g]) ? o[g] - sct[g] : -INFINITY;
         st_vec<G>(P + (size_t)row * G, out);
       };
-      sell_pass_log<G, L1C>(p.view[1], Q, x_s, partial, warp, lane, epi_bwd);
+      sell_pass_log<G, L1C, EMBED>(p.view[1], Q, x_s, partial, warp, lane, epi_bwd);
       if (p.view[1].n_split) { __syncthreads(); fixup_split_log<G>(p.view[1], partial, epi_bwd); }
       {  // this frame's gradient rows: one vector read per pdf, G coalesced row writes
         const float dead = as_log ? -INFINITY : 0.f;
@@ -408,23 +424,23 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
 int launch_den_shared_log(const BlobHeader &h, const DenParams &p, int G, bool l1c, int grid, size_t smem,
                           cudaStream_t stream) {
   cudaError_t e;
-#define LAUNCH_LOG(GG, LL)                                                                                              \
-  do {                                                                                                                  \
-    e = cudaFuncSetAttribute(den_shared_log_kernel<GG, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    if (e != cudaSuccess) return (int)e;                                                                                \
-    den_shared_log_kernel<GG, LL><<<grid, DEN_NT, smem, stream>>>(p);                                                   \
+#define LAUNCH_LOG(GG, LL, EE)                                                                                              \
+  do {                                                                                                                      \
+    e = cudaFuncSetAttribute(den_shared_log_kernel<GG, LL, EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e != cudaSuccess) return (int)e;                                                                                    \
+    den_shared_log_kernel<GG, LL, EE><<<grid, DEN_NT, smem, stream>>>(p);                                                   \
   } while (0)
-  if (l1c) {
-    if (G == 4) LAUNCH_LOG(4, true);
-    else if (G == 2) LAUNCH_LOG(2, true);
-    else LAUNCH_LOG(1, true);
-  } else {
-    if (G == 4) LAUNCH_LOG(4, false);
-    else if (G == 2) LAUNCH_LOG(2, false);
-    else LAUNCH_LOG(1, false);
-  }
+#define LAUNCH_LOG_G(GG)                                       \
+  do {                                                         \
+    if (h.embed_codes) LAUNCH_LOG(GG, false, true);            \
+    else if (l1c) LAUNCH_LOG(GG, true, false);                 \
+    else LAUNCH_LOG(GG, false, false);                         \
+  } while (0)
+  if (G == 4) LAUNCH_LOG_G(4);
+  else if (G == 2) LAUNCH_LOG_G(2);
+  else LAUNCH_LOG_G(1);
+#undef LAUNCH_LOG_G
 #undef LAUNCH_LOG
-  (void)h;
   return (int)cudaGetLastError();
 }
 

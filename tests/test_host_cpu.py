@@ -136,20 +136,23 @@ def test_graph_batch_layouts_and_reorder():
 
 def _parse_blob(blob):
     h = blob.numpy().tobytes()
-    magic, version, S, K, D, nw, S_pad, D_pad, max_sub, _, opt_g, C, C_pad, R_pad = struct.unpack_from("<II12i", h, 0)
-    views, off = [], 56
+    (magic, version, S, K, D, nw, S_pad, D_pad, max_sub, _, opt_g, C, C_pad, R_pad, embed, _r) = struct.unpack_from(
+        "<II14i", h, 0)
+    views, off = [], 64
     for i in range(5):
         n_rows, n_slices, n_split, n_sub, n_recs, o_info, o_rows, o_recs, o_split = struct.unpack_from("<4i5q", h, off)
         off += 56
         info = np.frombuffer(h, np.int64, nw * 3, o_info).reshape(nw, 3)
-        rows = np.zeros(0, np.int32)   # row codes travel inside the record streams
+        # embedded format: row codes travel inside the record streams; compact format: a parallel stream
+        rows = np.zeros(0, np.int32) if embed else np.frombuffer(h, np.int32, (n_slices + 3 * nw) * 32, o_rows)
         recs = np.frombuffer(h, np.uint32, n_recs * 2, o_recs).reshape(-1, 2)
         split = np.frombuffer(h, np.int32, n_split * 3, o_split).reshape(-1, 3)
-        views.append(dict(n_rows=n_rows, n_slices=n_slices, n_sub=n_sub, info=info, rows=rows, recs=recs, split=split))
+        views.append(dict(n_rows=n_rows, n_slices=n_slices, n_sub=n_sub, info=info, rows=rows, recs=recs, split=split,
+                          embed=embed))
     o_leaky, o_init, o_final, o_cd, o_cp, total = struct.unpack_from("<6q", h, off)
     pred = struct.unpack_from("<10d", h, off + 48)
     return dict(S=S, K=K, D=D, nw=nw, max_sub=max_sub, views=views, total=total, pred=pred, C=C, C_pad=C_pad,
-                S_pad=S_pad, R_pad=R_pad, version=version,
+                S_pad=S_pad, R_pad=R_pad, version=version, embed=embed,
                 cls_dst=np.frombuffer(h, np.int32, C, o_cd), cls_pdf=np.frombuffer(h, np.int32, C, o_cp),
                 leaky=np.frombuffer(h, np.float32, S, o_leaky), final=np.frombuffer(h, np.float32, S, o_final),
                 init=np.frombuffer(h, np.float32, S, o_init))
@@ -157,16 +160,19 @@ def _parse_blob(blob):
 
 def _decode_view(v, nw):
     """Walk the per-warp streams exactly like sell_pass does: returns {(row, a, b, w) multiset}.  Slots come in
-    pairs, [pair][lane][2]; the second slot of a slice's last pair is the lane's row code (sign bit of its weight
-    word), everything else is an arc (weight 0 = idle)."""
+    pairs, [pair][lane][2]; the sign bit of the second slot's weight word ends a slice (warp-uniform).  Embedded
+    format: that slot is the lane's row code; compact format: it is still an arc and the row codes come from the
+    parallel per-warp stream.  Weight 0 = idle slot."""
     out = []
     sub_owner = {}
     for row, first, cnt in v["split"]:
         for j in range(cnt):
             sub_owner[first + j] = row
+    embed = v["embed"]
     slices_seen = 0
     for w in range(nw):
-        rec0, npairs, nsl = v["info"][w]
+        rec0, npairs, third = v["info"][w]
+        rp = third
         pending = [[] for _ in range(32)]
         seen_w = 0
         for j in range(npairs):
@@ -175,23 +181,25 @@ def _decode_view(v, nw):
             assert flags.min() == flags.max(), "end-of-slice flag must be warp-uniform"
             for lane in range(32):
                 for slot in range(2):
-                    if slot == 1 and flags[0]:
+                    if slot == 1 and flags[0] and embed:
                         continue
                     ab, wb = int(blk[lane, slot, 0]), int(blk[lane, slot, 1])
-                    assert not (wb >> 31), "arc weights are >= 0"
-                    wt = np.frombuffer(np.uint32(wb).tobytes(), np.float32)[0]
+                    assert not (wb >> 31) or (slot == 1 and not embed), "arc weights are >= 0"
+                    wt = np.frombuffer(np.uint32(wb & 0x7fffffff).tobytes(), np.float32)[0]
                     if wt != 0.0:
                         pending[lane].append((ab & 0xffff, ab >> 16, wt))
             if flags[0]:
                 slices_seen += 1
                 seen_w += 1
+                codes = blk[:, 1, 0].astype(np.int32) if embed else v["rows"][rp: rp + 32]
+                rp += 32
                 for lane in range(32):
-                    code = int(np.int32(blk[lane, 1, 0]))
+                    code = int(np.int32(codes[lane]))
                     row = (code & 0xfffff) if code >= 0 else ((sub_owner[-2 - code] & 0xfffff) if code <= -2 else None)
                     assert row is not None or not pending[lane]
                     out += [(row,) + t for t in pending[lane]]
                     pending[lane] = []
-        assert not any(pending) and seen_w == nsl
+        assert not any(pending) and (seen_w == third if embed else True)
     assert slices_seen == v["n_slices"]
     return sorted(out)
 
@@ -243,15 +251,17 @@ def _blob_forward_backward(b, x, coeff):
     v = [_decode_view(b["views"][i], b["nw"]) for i in range(5)]
     flagged = set()
     v1 = b["views"][1]
-    codes = [int(np.int32(c)) for c, wb in v1["recs"] if wb >> 31] + [int(r) for r, _, _ in v1["split"]]
-    for code in codes:
+    if b["embed"]:
+        codes = [int(np.int32(c)) for c, wb in v1["recs"] if wb >> 31]
+        for c, wb in v1["recs"]:   # the row-code slots of view 1 carry leaky(row)
+            if wb >> 31 and np.int32(c) >= 0:
+                lv = np.frombuffer(np.uint32(wb & 0x7fffffff).tobytes(), np.float32)[0]
+                assert lv == b["leaky"][int(np.int32(c)) & 0xfffff]
+    else:
+        codes = [int(c) for c in v1["rows"]]
+    for code in codes + [int(r) for r, _, _ in v1["split"]]:
         if code >= 0 and code & 0x40000000:
             flagged.add(code & 0xfffff)
-    # the row-code slots of view 1 carry leaky(row)
-    for c, wb in v1["recs"]:
-        if wb >> 31 and np.int32(c) >= 0:
-            lv = np.frombuffer(np.uint32(wb & 0x7fffffff).tobytes(), np.float32)[0]
-            assert lv == b["leaky"][int(np.int32(c)) & 0xfffff]
     assert flagged == {r for r, _, _, _ in v[4]}
     R = b["R_pad"]
 
@@ -298,7 +308,8 @@ def _blob_forward_backward(b, x, coeff):
 
 @pytest.mark.parametrize("variant,S,K,D,min_class", [("biphone", 150, 1400, 40, 4), ("biphone", 150, 1400, 40, 2),
                                                      ("uniform", 60, 900, 3, 2), ("skew", 80, 1500, 2, 3)])
-def test_den_packer_class_factorisation(variant, S, K, D, min_class):
+@pytest.mark.parametrize("embed", [0, 1])
+def test_den_packer_class_factorisation(variant, S, K, D, min_class, embed, monkeypatch):
     """(dst,pdf) classes: the packed views + class table reproduce the oracle's forward-backward exactly (up to
     float64 reordering) -- structured graphs (pdf a function of the destination), graphs where only some arcs
     share a class (few pdfs), and heavy rows split into sub-rows."""
@@ -306,14 +317,13 @@ def test_den_packer_class_factorisation(variant, S, K, D, min_class):
     g = ChainGraph(synth.random_den_fst(S, K, D, seed=19, variant=variant))
     gb = ChainGraphBatch(g, 1)
     gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_PROB)
-    os.environ["CHAIN_B200_MIN_CLASS"] = str(min_class)
-    try:
-        engine._prepared_cache.clear()
-        b = _parse_blob(engine.prepare_den_graph(gt, g.num_states, D, "cpu").blob_host)
-    finally:
-        os.environ.pop("CHAIN_B200_MIN_CLASS")
-        engine._prepared_cache.clear()
-    assert b["version"] == 12 and b["C"] > 0 and b["R_pad"] == b["S_pad"] + b["C_pad"]
+    monkeypatch.setenv("CHAIN_B200_MIN_CLASS", str(min_class))
+    monkeypatch.setenv("CHAIN_B200_EMBED_CODES", str(embed))    # both stream formats (den_blob.h)
+    engine._prepared_cache.clear()
+    b = _parse_blob(engine.prepare_den_graph(gt, g.num_states, D, "cpu").blob_host)
+    engine._prepared_cache.clear()
+    assert b["embed"] == embed
+    assert b["version"] == 13 and b["C"] > 0 and b["R_pad"] == b["S_pad"] + b["C_pad"]
     # every arc is either a two-operand record of views 0/1/2 or a member of exactly one class (views 3 and 4)
     n_cls_arcs = len(_decode_view(b["views"][3], 16))
     assert n_cls_arcs == len(_decode_view(b["views"][4], 16)) >= min_class * b["C"]

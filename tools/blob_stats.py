@@ -11,13 +11,13 @@ def stats(cfg, variant="uniform", B=None):
     engine._prepared_cache.clear()
     t = time.time(); prep = engine.prepare_den_graph(gt, g.num_states, c["D"], "cpu", batch_size=B or c["B"]); dt = time.time() - t
     h = prep.blob_host.numpy()
-    hdr = struct.unpack_from("<II12i", h, 0)
-    opt_g, C, C_pad, R_pad, max_sub = hdr[10], hdr[11], hdr[12], hdr[13], hdr[8]
-    off = 56; out = []
+    hdr = struct.unpack_from("<II14i", h, 0)
+    opt_g, C, C_pad, R_pad, max_sub, embed = hdr[10], hdr[11], hdr[12], hdr[13], hdr[8], hdr[14]
+    off = 64; out = []
     for i in range(5):
         v = struct.unpack_from("<4i5q", h, off); off += 56; out.append(v)
     tail = struct.unpack_from("<6q10d", h, off)
-    print(f"{cfg} {variant} G={opt_g}: pack {dt:.2f}s; classes C={C} (R_pad={R_pad}), max_sub={max_sub}, blob {tail[5]/1e6:.2f} MB")
+    print(f"{cfg} {variant} G={opt_g}: pack {dt:.2f}s; classes C={C} (R_pad={R_pad}), max_sub={max_sub}, {'embedded row codes' if embed else 'compact streams'}, blob {tail[5]/1e6:.2f} MB")
     tot_wf = 0
     for i in range(5):
         wf, ideal = tail[6 + i], tail[11 + i]
