@@ -558,21 +558,27 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
     }
   }
   for (int c = 0; c < C; c++) a2.push(cls[c].pdf, (uint32_t)(S_pad + c) | ((uint32_t)cls[c].dst << 16), one);
-  // Stream format: a slice of one arc pair or less leaves the separate row-code stream (read two slices ahead) no
-  // time to cover its L2 latency -- chain graphs, whose states keep a self loop and one class arc, are made of such
-  // slices -- so their row codes travel inside the record streams (one extra slot per slice); graphs with fat
-  // slices keep the compact format, where that slot would be pure overhead (measured: cfg5, 5 arcs per state, 1.41 ms
-  // compact vs 1.67 ms embedded; cfg4 biphone 7.2 ms compact vs 6.3 ms embedded).
+  // Stream format (den_blob.h).  Embedded row codes cost one slot per slice but (i) slices of one arc pair or less --
+  // chain graphs, whose states keep a self loop and one class arc, are made of them -- leave a separate row-code
+  // stream, read two slices ahead, no time to cover its L2 latency, and (ii) the code stream's registers are what the
+  // G = 4 kernel is short of.  Measured on B200, ms per call, embedded / compact: cfg4 biphone 5.85 / 6.97, cfg4 skew
+  // 8.93 / 9.66, cfg4 uniform 8.00 / 8.63, cfg5 (5 arcs per state: 3 pairs per slice) 1.67 / 1.59.  So: compact only
+  // for graphs of fat-free, SHORT slices, where the extra slot is a sixth of the stream.
   {
-    auto thin_fraction = [&](int n_rows, const ArcSet &as) {
+    auto slice_stats = [&](int n_rows, const ArcSet &as, double &thin_frac, double &pairs_per_slice) {
       std::vector<int> deg(n_rows, 0);
       for (int r : as.row_of) deg[r]++;
       std::sort(deg.begin(), deg.end(), std::greater<int>());
       int thin = 0, n_sl = 0;
-      for (int i = 0; i < n_rows; i += 32, n_sl++) thin += deg[i] <= 2;   // the slice's longest row: <= one pair
-      return n_sl ? (double)thin / n_sl : 0.0;
+      long pairs = 0;
+      for (int i = 0; i < n_rows; i += 32, n_sl++) { thin += deg[i] <= 2; pairs += (deg[i] + 1) / 2; }
+      thin_frac = n_sl ? (double)thin / n_sl : 0.0;
+      pairs_per_slice = n_sl ? (double)pairs / n_sl : 0.0;
     };
-    embed = std::max(thin_fraction(S, a0), thin_fraction(S, a1)) > 0.25;
+    double t0, p0, t1, p1;
+    slice_stats(S, a0, t0, p0);
+    slice_stats(S, a1, t1, p1);
+    embed = std::max(t0, t1) > 0.25 || 0.5 * (p0 + p1) >= 3.5;
     if (const char *e = getenv("CHAIN_B200_EMBED_CODES")) embed = atoi(e) != 0;
   }
   for (int i = 0; i < kNumViews; i++) vb[i] = ViewBuild();

@@ -7,7 +7,7 @@ timeout 300 python bench.py --gpus 1 --config cfg5 --scaling strong $Q > gpurun_
 for n in 2 4 8; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500+n)) bench.py --gpus $n --config cfg5 --scaling strong $Q > gpurun_out/r2_strong_cfg5_n$n.json 2> gpurun_out/r2_strong_cfg5_n$n.err
 done
-for n in 2 8; do
+for n in 8; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600+n)) bench.py --gpus $n $Q > gpurun_out/r2_weak_cfg4_n$n.json 2> gpurun_out/r2_weak_cfg4_n$n.err
 done
 for f in gpurun_out/r2_strong_cfg5_n*.json gpurun_out/r2_weak_cfg4_n*.json; do echo -n "$f  "; python -c "
