@@ -130,9 +130,9 @@ def workload_name(cfg, variant, c):
 
 def config_dict(a, spec, world):
     """ONE definition of `config` for both arms (the driver compares them key by key)."""
-    B, T, D, S = spec["B"], spec["T"], spec["D"], spec["S"]
-    return {"workload": workload_name(a.config, a.variant, spec), "global_batch": B * world,
-            "frames_per_step": frames_of(spec) * world,
+    B, T, D, S = spec["shard"][1], spec["T"], spec["D"], spec["S"]
+    return {"workload": workload_name(a.config, a.variant, dict(spec, B=B)), "global_batch": B * world,
+            "frames_per_step": frames_of(spec) * (world if a.scaling == "weak" else 1),
             "scaling": a.scaling,
             "parallelism": "batch-shard x%d, one NCCL sum of {objf,frames,ok}" % world,
             "l2": "inputs (%.0f MB x + %.0f MB alpha spill per step) exceed the 126 MB L2; no flush needed" % (
@@ -145,11 +145,19 @@ def frames_of(spec):
 
 
 def make_spec(a, rank, world):
+    """Weak scaling: every rank owns its own batch of the config's size (seeds differ per rank).  Strong scaling: ONE
+    global batch (the config's B_global, cfg5: 4096; rank 0's seeds) of which rank r takes the contiguous shard
+    [r*B/W, (r+1)*B/W) -- `shard` = (start, count) inside that batch; the summed objf is then the same for every W."""
     from pychain_b200 import synth
-    spec = synth.workload_spec(a.config, a.variant, rank)
-    if a.scaling == "strong":   # the global batch of the config is fixed and split over the ranks (cfg5: 4096)
+    if a.scaling == "strong":
+        spec = synth.workload_spec(a.config, a.variant, 0)
         gb = synth.CONFIGS[a.config].get("B_global", spec["B"])
-        spec["B"] = gb // world
+        spec["B"] = gb
+        per = gb // world
+        spec["shard"] = (rank * per, per)
+    else:
+        spec = synth.workload_spec(a.config, a.variant, rank)
+        spec["shard"] = (0, spec["B"])
     return spec
 
 
@@ -271,8 +279,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     spec = make_spec(a, rank, world)
-    graph, num_batch, x_host, lengths = synth.build_workload(spec)
-    B, T, D, S, K = spec["B"], spec["T"], spec["D"], spec["S"], spec["K"]
+    graph, num_batch, x_host, lengths = synth.build_workload(spec, *spec["shard"])
+    B, T, D, S, K = spec["shard"][1], spec["T"], spec["D"], spec["S"], spec["K"]
     mode = spec["mode"]
     gb = ChainGraphBatch(graph, B)
     gt = tuple(getattr(gb, n) for n in (engine._GRAPH_NAMES_LOG if mode == "logden" else engine._GRAPH_NAMES_PROB))

@@ -34,6 +34,16 @@ __device__ __forceinline__ void lse_rec(const uint32_t ab, const float w, const 
   for (int g = 0; g < G; g++) lse_add_fast(m[g], s[g], a[g] + w + b[g]);
 }
 
+// Two terms folded into the running (max, sum-exp) at once: three exponentials instead of four and ONE step of the
+// lane's serial dependency chain per record pair instead of two (t1 = -inf: "no second term").
+__device__ __forceinline__ void lse_add2_fast(float &m, float &s, float t0, float t1) {
+  const float M = fmaxf(m, fmaxf(t0, t1));
+  if (M > -INFINITY) {
+    s = s * __expf(m - M) + __expf(t0 - M) + __expf(t1 - M);
+    m = M;
+  }
+}
+
 // One SELL pass in the log semiring: every lane folds A[a_k][g] + w_k + Bv[b_k][g] of its
 // row's records into a running (max, sum-exp) per utterance.  Record streams and the
 // two-bank register prefetch are those of den_shared.cu; the end-of-slice flag is bit 31 of
@@ -61,9 +71,24 @@ __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__res
   for (int g = 0; g < G; g++) { m[g] = -INFINITY; s[g] = 0.f; }
   // a pair is two arcs, or -- at the end of a slice -- an arc and the lane's row-code slot (weight word = kCodeMarkLog)
   auto process = [&](const uint2 r0, const uint2 r1) {
-    lse_rec<G>(r0.x, __uint_as_float(r0.y), A, Bv, m, s);
     const bool last = EMBED ? (r1.y == kCodeMarkLog) : ((r1.x & 0x80000000u) != 0);  // warp-uniform: end of the slice
-    if (!EMBED) lse_rec<G>(r1.x & 0x7fffffffu, __uint_as_float(r1.y), A, Bv, m, s);
+    {
+      float a0[G], b0[G], t1[G];
+      ld_vec<G>(A + (r0.x & 0xffffu) * G, a0);
+      ld_vec<G>(Bv + (r0.x >> 16) * G, b0);
+#pragma unroll
+      for (int g = 0; g < G; g++) t1[g] = -INFINITY;
+      if (!EMBED || !last) {   // the second slot is an arc (compact format: always; embedded: unless it is the row code)
+        float a1[G], b1[G];
+        const uint32_t x1 = EMBED ? r1.x : (r1.x & 0x7fffffffu);
+        ld_vec<G>(A + (x1 & 0xffffu) * G, a1);
+        ld_vec<G>(Bv + (x1 >> 16) * G, b1);
+#pragma unroll
+        for (int g = 0; g < G; g++) t1[g] = a1[g] + __uint_as_float(r1.y) + b1[g];
+      }
+#pragma unroll
+      for (int g = 0; g < G; g++) lse_add2_fast(m[g], s[g], a0[g] + __uint_as_float(r0.y) + b0[g], t1[g]);
+    }
     if (last) {
       const int row = EMBED ? (int)r1.x : row_c;
       if (row >= 0) {
@@ -83,8 +108,6 @@ __device__ __forceinline__ void sell_pass_log(const DView &v, const float *__res
         row_n2 = __ldg(rp);
         rp += 32;
       }
-    } else if (EMBED) {
-      lse_rec<G>(r1.x, __uint_as_float(r1.y), A, Bv, m, s);
     }
   };
   int j = 0;
