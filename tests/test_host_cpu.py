@@ -368,3 +368,48 @@ def test_product_never_touches_the_oracle():
                 assert "chain_oracle" not in code and "oracle/_ref" not in code, (f, line)
     hdr = open(os.path.join(ROOT, "include", "chain_b200.h")).read()
     assert "NO CPU implementation" in hdr
+
+
+def test_shared_batch_to_keeps_stride0_and_reorder_keeps_device():
+    """`.to(device)` of a shared (stride-0) batch must not materialise B copies, and `reorder` must
+    stay on that device."""
+    g = ChainGraph(synth.random_den_fst(12, 40, 8, seed=3))
+    gb = ChainGraphBatch(g, 5).to(torch.device("cpu"))
+    assert gb.shared_graph is g
+    for name in engine._GRAPH_NAMES_PROB:
+        t = getattr(gb, name)
+        assert t.size(0) == 5 and t.stride(0) == 0
+    gb.reorder(torch.tensor([2, 0, 1]))
+    assert gb.batch_size == 3 and gb.forward_transitions.stride(0) == 0 and gb.start_state.numel() == 3
+    assert engine._is_shared(tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_PROB), 3)
+
+
+def test_fst_from_text_formats():
+    """acceptor-format text must not be misread as transducer text (and vice versa)."""
+    tr = ["0 1 3 3 0.5", "1 1 2 2 0.25", "1 0.125"]
+    f = Fst.from_text(tr)
+    assert f.num_states() == 2 and f.num_arcs == 2 and list(f.pdf) == [2, 1]
+    assert np.allclose(f.log_weight, [-0.5, -0.25]) and np.isclose(f.final_log_weight[1], -0.125)
+    ac = ["0 1 3 0.5", "1 1 2 0.25", "1 0.125"]
+    fa = Fst.from_text(ac, acceptor=True)
+    assert list(fa.pdf) == [2, 1] and np.allclose(fa.log_weight, [-0.5, -0.25])
+    with pytest.raises(ValueError):
+        Fst.from_text(["0 1 3", "1"])                       # 3 fields: acceptor text without the flag
+    with pytest.raises(ValueError):
+        Fst.from_text(["0 1 3 0.5"], acceptor=False)        # olabel is not an integer
+    with pytest.raises(ValueError):
+        Fst.from_text(["0 1 3 3 0.5 7"])                    # too many fields
+
+
+def test_materialised_batch_detection_host_side():
+    """A materialised batch of identical rows is recognised (rows 0, B//2, B-1 of every tensor); one differing row
+    at a sampled position, or a per-utterance batch, is not."""
+    g = ChainGraph(synth.random_den_fst(12, 40, 8, seed=3))
+    mat = ChainGraphBatch(g, 6).materialize()
+    gt = tuple(getattr(mat, n) for n in engine._GRAPH_NAMES_PROB)
+    rows, key = engine._shared_rows(gt, 6)
+    assert rows is not None and key is not None and rows[0].shape[0] == 1
+    mat.forward_transition_probs[3] *= 0.5
+    assert engine._shared_rows(tuple(getattr(mat, n) for n in engine._GRAPH_NAMES_PROB), 6) == (None, None)
+    nb = synth.make_num_batch(4, 30, 8, seed=1, min_phones=2, max_phones=4)
+    assert engine._shared_rows(tuple(getattr(nb, n) for n in engine._GRAPH_NAMES_LOG), 4) == (None, None)
