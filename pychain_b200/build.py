@@ -46,18 +46,34 @@ def build_variant(name, defines):
 
 
 def build(force=False, verbose=False):
+    """One `nvcc -c` per source (in parallel), then one link: libchain_b200.so."""
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB] + _sources()
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    log = r.stdout + r.stderr
-    with open(os.path.join(PKG, "lib", "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if verbose or r.returncode != 0:
+    libdir = os.path.dirname(LIB)
+    objdir = os.path.join(libdir, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    inc = ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    jobs = []
+    for src in _sources():
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + inc + ["-c", src, "-o", obj]
+        jobs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log, failed = "", False
+    for cmd, obj, p in jobs:
+        out = p.communicate()[0]
+        log += " ".join(cmd) + "\n" + out
+        failed |= p.returncode != 0
+    if not failed:
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + [j[1] for j in jobs]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log += " ".join(cmd) + "\n" + r.stdout + r.stderr
+        failed = r.returncode != 0
+    with open(os.path.join(libdir, "build.log"), "w") as f:
+        f.write(log)
+    if verbose or failed:
         print(log)
-    if r.returncode != 0:
+    if failed:
         raise RuntimeError("nvcc failed building libchain_b200.so")
     return LIB
 
