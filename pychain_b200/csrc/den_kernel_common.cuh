@@ -29,7 +29,10 @@ struct DenParams {
   float grad_scale;    // posteriors are multiplied by this as they are written
   float *logp, *grad, *diag;
   float *alpha_ws, *tot_ws;
-  int num_groups, use_tma_x;
+  int num_groups, use_tma_x, max_sub;
+  // records resident in shared memory (small graphs): byte offset of every warp's slot stream of every view inside
+  // the CTA's record area (which follows the split-row slots), filled by the launcher from the host blob
+  uint32_t rs_off[kNumViews][DEN_NW];
   int n_rep;           // copies of the blob laid out back to back on the device
   size_t rep_stride;   // bytes between copies
 };
@@ -184,6 +187,20 @@ inline int choose_G(const BlobHeader &h, int B, int num_sms) {
 
 // defined in den_shared_log.cu
 int launch_den_shared_log(const BlobHeader &h, const DenParams &p, int G, bool l1c, int grid, size_t smem, cudaStream_t stream);
+
+// Bytes of the slot streams proper (without the register-bank run-out) of all views: what a CTA copies into shared
+// memory when the graph is small enough to keep its records there.  Fills the per-warp offsets.
+inline size_t resident_record_bytes(const void *blob_host, const BlobHeader &h, uint32_t (*off)[DEN_NW]) {
+  size_t total = 0;
+  for (int v = 0; v < kNumViews; v++) {
+    const int64_t *wi = (const int64_t *)((const char *)blob_host + h.view[v].off_warp_info);
+    for (int w = 0; w < DEN_NW; w++) {
+      if (off) off[v][w] = (uint32_t)total;
+      total += (size_t)wi[3 * w + 1] * 512;   // pairs x 32 lanes x 16 bytes
+    }
+  }
+  return total;
+}
 
 // Do the record streams of all three views fit in L1 next to the CTA's shared memory?
 inline bool records_fit_l1(const BlobHeader &h, size_t smem) {

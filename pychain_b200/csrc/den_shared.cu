@@ -127,20 +127,25 @@ __device__ __forceinline__ void consume_rec1(const uint32_t ab, const float w, c
 // EMBED: stream format of the blob (den_blob.h): row codes in the last slot of every slice, or (compact format)
 // a parallel stream `rp` of row codes read two slices ahead, the slice ending on the sign bit of its last arc's
 // weight and the epilogue's per-row float coming from `aux_tab`.
+// RES (= L1C && EMBED): the graph is small enough for its slot streams to live in shared memory (copied once per CTA,
+// `sp_s`): a pair is one 128-bit LDS away, there is no L2 latency to hide and no register banks.
 template <int G, bool L1C, bool EMBED, bool ONE, int NF, class Epi>
-__device__ CHAIN_B200_PASS_ATTR Epi sell_pass(const uint4 *__restrict__ sp, const int npairs, const uint32_t A_s,
-                                      const uint32_t B_s, const uint32_t amax, const uint32_t bmax,
+__device__ CHAIN_B200_PASS_ATTR Epi sell_pass(const uint4 *__restrict__ sp, const uint32_t sp_s, const int npairs,
+                                      const uint32_t A_s, const uint32_t B_s, const uint32_t amax, const uint32_t bmax,
                                       const uint32_t part_s, const int32_t *__restrict__ rp,
                                       const float *__restrict__ aux_tab, Epi epi) {
-  uint4 fa[NF], fb[NF];
+  constexpr bool RES = L1C && EMBED;
+  uint4 fa[RES ? 1 : NF], fb[RES ? 1 : NF];
   int row = 0, row_n1 = 0, row_n2 = 0;
   if constexpr (!EMBED) {
     row = __ldg(rp); row_n1 = __ldg(rp + 32); row_n2 = __ldg(rp + 64);
     rp += 96;
   }
+  if constexpr (!RES) {
 #pragma unroll
-  for (int d = 0; d < NF; d++) fa[d] = ldg_stream<L1C>(sp + d * 32);
-  sp += NF * 32;
+    for (int d = 0; d < NF; d++) fa[d] = ldg_stream<L1C>(sp + d * 32);
+    sp += NF * 32;
+  }
   float acc[G];
 #pragma unroll
   for (int g = 0; g < G; g++) acc[g] = 0.f;
@@ -194,6 +199,24 @@ __device__ CHAIN_B200_PASS_ATTR Epi sell_pass(const uint4 *__restrict__ sp, cons
       for (int g = 0; g < G; g++) asm volatile("" : "+f"(acc[g]));
     }
   };
+  if constexpr (RES) {
+    uint32_t at = sp_s;
+    int j = 0;
+    for (; j + 4 <= npairs; j += 4, at += 4 * 512) {   // four pairs' slots fetched together, then consumed
+      uint4 q[4];
+#pragma unroll
+      for (int d = 0; d < 4; d++)
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q[d].x), "=r"(q[d].y), "=r"(q[d].z), "=r"(q[d].w) : "r"(at + d * 512));
+#pragma unroll
+      for (int d = 0; d < 4; d++) process(make_uint2(q[d].x, q[d].y), make_uint2(q[d].z, q[d].w));
+    }
+    for (; j < npairs; j++, at += 512) {
+      uint4 q;
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(at));
+      process(make_uint2(q.x, q.y), make_uint2(q.z, q.w));
+    }
+    return epi;
+  }
   int j = 0;
   for (; j + 2 * NF <= npairs; j += 2 * NF) {  // full double banks: straight-line code
 #pragma unroll
@@ -227,12 +250,13 @@ __device__ CHAIN_B200_PASS_ATTR Epi sell_pass(const uint4 *__restrict__ sp, cons
 
 // Launch one pass for this warp: stream start / length of view `v`.
 template <int G, bool L1C, bool EMBED, bool ONE, int NF, class Epi>
-__device__ __forceinline__ Epi run_pass(const DView &v, uint32_t A_s, uint32_t B_s, uint32_t amax, uint32_t bmax,
-                                        uint32_t part_s, const float *aux_tab, int warp, int lane, Epi epi) {
+__device__ __forceinline__ Epi run_pass(const DView &v, uint32_t rec_s /* this warp's resident stream of the view */,
+                                        uint32_t A_s, uint32_t B_s, uint32_t amax, uint32_t bmax, uint32_t part_s,
+                                        const float *aux_tab, int warp, int lane, Epi epi) {
   const uint4 *sp = reinterpret_cast<const uint4 *>(v.recs + v.warp_info[3 * warp]) + lane;  // [pair][lane]: 2 slots
   const int32_t *rp = EMBED ? nullptr : v.rows + v.warp_info[3 * warp + 2] + lane;
-  return sell_pass<G, L1C, EMBED, ONE, NF, Epi>(sp, (int)v.warp_info[3 * warp + 1], A_s, B_s, amax, bmax, part_s, rp,
-                                                aux_tab, epi);
+  return sell_pass<G, L1C, EMBED, ONE, NF, Epi>(sp, rec_s + lane * 16u, (int)v.warp_info[3 * warp + 1], A_s, B_s, amax,
+                                                bmax, part_s, rp, aux_tab, epi);
 }
 
 // ---- the epilogues of the five passes: what happens to a finished row --------------------------------------
@@ -330,6 +354,8 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
   float *gam_s = xraw + (size_t)D_pad * G;
   float *partial = gam_s + (size_t)D_pad * G;
   const uint32_t part_sa = smem_u32(partial);
+  // records resident in shared memory (small graphs): the area after the split-row slots, 16-byte aligned
+  const uint32_t rec_sa = (smem_u32(partial + (size_t)p.max_sub * G) + 15u) & ~15u;
   const float *__restrict__ lk = p.leaky;
   const float *__restrict__ ini = p.init;
   const float *__restrict__ fin = p.fin;
@@ -338,6 +364,18 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
 
   // the packed views are read straight from the kernel parameters (constant bank): no registers held
   const DView *views = p.view;
+  if constexpr (L1C && EMBED) {   // every warp brings in the slot streams it will walk, once
+    for (int v = 0; v < kNumViews; v++) {
+      const uint4 *src = reinterpret_cast<const uint4 *>(views[v].recs + views[v].warp_info[3 * warp]);
+      const int n = (int)views[v].warp_info[3 * warp + 1] * 32;
+      const uint32_t dst = rec_sa + p.rs_off[v][warp];
+      for (int i = lane; i < n; i += 32) {
+        const uint4 q = __ldg(src + i);
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)i * 16u), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+      }
+    }
+    __syncwarp();
+  }
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
@@ -457,7 +495,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         // class sums A_c(t-1) = sum_{arcs of class c} alpha'(t-1,src) * w: one operand per arc.  They extend the
         // state row (virtual states S_pad + c) and are spilled with it: the backward pass needs them again.
         EpiClass<G> epi_cls{smem_u32(A + (size_t)S_pad * G), aws + ((size_t)(t - 1) * R_pad + S_pad) * G};
-        epi_cls = run_pass<G, L1C, EMBED, true, nf1<G>()>(views[3], smem_u32(A), 0u, S - 1, 0, part_sa, nullptr, warp, lane, epi_cls);
+        epi_cls = run_pass<G, L1C, EMBED, true, nf1<G>()>(views[3], rec_sa + p.rs_off[3][warp], smem_u32(A), 0u, S - 1, 0, part_sa, nullptr, warp, lane, epi_cls);
         if (p.view[3].n_split) { __syncthreads(); fixup_split<G>(p.view[3], partial, nullptr, epi_cls); }
       }
       __syncthreads();  // x_s complete, xraw free, class sums complete
@@ -466,7 +504,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       epi_fwd.out_s = smem_u32(Bn);
 #pragma unroll
       for (int g = 0; g < G; g++) epi_fwd.part[g] = 0.f;
-      epi_fwd = run_pass<G, L1C, EMBED, false, nf2a<G>()>(views[0], smem_u32(A), smem_u32(x_s), R_pad - 1, D - 1,
+      epi_fwd = run_pass<G, L1C, EMBED, false, nf2a<G>()>(views[0], rec_sa + p.rs_off[0][warp], smem_u32(A), smem_u32(x_s), R_pad - 1, D - 1,
                                                           part_sa, nullptr, warp, lane, epi_fwd);
       if (p.view[0].n_split) { __syncthreads(); fixup_split<G>(p.view[0], partial, nullptr, epi_fwd); }
 #pragma unroll
@@ -586,7 +624,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
 
       // ---- gamma pass: rows = pdfs; gamma(t,n) = x(t,n)/tot(t) * sum alpha'(src) p beta(dst)
       EpiGamma<G> epi_gam{smem_u32(x_s), smem_u32(gam_s)};
-      epi_gam = run_pass<G, L1C, EMBED, false, nf2<G>()>(views[2], smem_u32(P), smem_u32(Q), R_pad - 1, S - 1,
+      epi_gam = run_pass<G, L1C, EMBED, false, nf2<G>()>(views[2], rec_sa + p.rs_off[2][warp], smem_u32(P), smem_u32(Q), R_pad - 1, S - 1,
                                                           part_sa, nullptr, warp, lane, epi_gam);
       if (p.view[2].n_split) { __syncthreads(); fixup_split<G>(p.view[2], partial, nullptr, epi_gam); }
       __syncthreads();  // gamma rows complete; everybody done reading P; bx complete
@@ -594,7 +632,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       // ---- beta' pass, class arcs: rows = source states, one operand (bx_c) per arc; the raw sums wait in P
       if (C) {
         EpiStore<G> epi_b2{smem_u32(P)};
-        epi_b2 = run_pass<G, L1C, EMBED, true, nf1<G>()>(views[4], smem_u32(Q), 0u, R_pad - 1, 0, part_sa, nullptr, warp, lane, epi_b2);
+        epi_b2 = run_pass<G, L1C, EMBED, true, nf1<G>()>(views[4], rec_sa + p.rs_off[4][warp], smem_u32(Q), 0u, R_pad - 1, 0, part_sa, nullptr, warp, lane, epi_b2);
         if (p.view[4].n_split) { __syncthreads(); fixup_split<G>(p.view[4], partial, nullptr, epi_b2); }
         __syncthreads();
       }
@@ -604,7 +642,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       epi_bwd.out_s = smem_u32(P);
 #pragma unroll
       for (int g = 0; g < G; g++) epi_bwd.lpart[g] = 0.f;
-      epi_bwd = run_pass<G, L1C, EMBED, false, nf2<G>()>(views[1], smem_u32(Q), smem_u32(x_s), S - 1, D - 1,
+      epi_bwd = run_pass<G, L1C, EMBED, false, nf2<G>()>(views[1], rec_sa + p.rs_off[1][warp], smem_u32(Q), smem_u32(x_s), S - 1, D - 1,
                                                           part_sa, lk, warp, lane, epi_bwd);
       if (p.view[1].n_split) { __syncthreads(); fixup_split<G>(p.view[1], partial, lk, epi_bwd); }
 #pragma unroll
@@ -750,6 +788,12 @@ int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev,
 
   const int grid = std::min(p.num_groups, num_sms);
   const bool l1c = records_fit_l1(h, smem) && !getenv("CHAIN_B200_NO_L1_RECORDS");
+  // small graphs in the embedded stream format keep their slot streams in shared memory (copied once per CTA)
+  p.max_sub = h.max_sub;
+  const size_t rec_bytes = resident_record_bytes(blob_host, h, p.rs_off);
+  const bool res = h.embed_codes && !h.log_domain && smem + rec_bytes + 16 <= (size_t)227 * 1024 &&
+                   !getenv("CHAIN_B200_NO_RESIDENT_RECORDS");
+  const size_t smem_launch = smem + (res ? rec_bytes + 16 : 0);
   cudaError_t e;
   if (h.log_domain) {  // same blob layout, log semiring (den_shared_log.cu)
     const int st = launch_den_shared_log(h, p, G, l1c, grid, smem, stream);
@@ -761,13 +805,15 @@ int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev,
   }
 #define LAUNCH_DEN(GG, LL, EE)                                                                                         \
   do {                                                                                                                \
-    e = cudaFuncSetAttribute(den_shared_kernel<GG, LL, EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    e = cudaFuncSetAttribute(den_shared_kernel<GG, LL, EE>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                             (int)smem_launch);                                                                       \
     if (e != cudaSuccess) return (int)e;                                                                              \
-    den_shared_kernel<GG, LL, EE><<<grid, DEN_NT, smem, stream>>>(p);                                                 \
+    den_shared_kernel<GG, LL, EE><<<grid, DEN_NT, smem_launch, stream>>>(p);                                          \
   } while (0)
 #define LAUNCH_DEN_G(GG)                                       \
   do {                                                         \
-    if (h.embed_codes) LAUNCH_DEN(GG, false, true);            \
+    if (h.embed_codes && res) LAUNCH_DEN(GG, true, true);      \
+    else if (h.embed_codes) LAUNCH_DEN(GG, false, true);       \
     else if (l1c) LAUNCH_DEN(GG, true, false);                 \
     else LAUNCH_DEN(GG, false, false);                         \
   } while (0)
