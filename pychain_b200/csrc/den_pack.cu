@@ -475,6 +475,7 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
   const int S_pad = (S + 3) / 4 * 4, D_pad = (D + 3) / 4 * 4;
   const bool so = (out == nullptr);
   bool embed = false;   // stream format (den_blob.h), decided below from how thin the slices of views 0 and 1 are
+  bool tried_resident = false, no_resident = log_domain;   // (the log-domain kernel streams; it has no resident mode)
 
   // ---- (dst, pdf) classes: the arcs of one destination that share a pdf (see den_blob.h) ----------------
   // candidates in backward-CSR order (arcs grouped by destination), members keep their CSR order
@@ -562,8 +563,9 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
   // chain graphs, whose states keep a self loop and one class arc, are made of them -- leave a separate row-code
   // stream, read two slices ahead, no time to cover its L2 latency, and (ii) the code stream's registers are what the
   // G = 4 kernel is short of.  Measured on B200, ms per call, embedded / compact: cfg4 biphone 5.85 / 6.97, cfg4 skew
-  // 8.93 / 9.66, cfg4 uniform 8.00 / 8.63, cfg5 (5 arcs per state: 3 pairs per slice) 1.67 / 1.59.  So: compact only
-  // for graphs of fat-free, SHORT slices, where the extra slot is a sixth of the stream.
+  // 8.93 / 9.66, cfg4 uniform 8.00 / 8.63, cfg5 (5 arcs per state: 3 pairs per slice) 1.67 / 1.59 streamed from L2 --
+  // but 1.50 embedded and RESIDENT in shared memory.  So: compact only for mid-size graphs of fat-free, SHORT slices,
+  // where the extra slot is a sixth of the stream and the streams do not fit on chip.
   {
     auto slice_stats = [&](int n_rows, const ArcSet &as, double &thin_frac, double &pairs_per_slice) {
       std::vector<int> deg(n_rows, 0);
@@ -578,7 +580,12 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
     double t0, p0, t1, p1;
     slice_stats(S, a0, t0, p0);
     slice_stats(S, a1, t1, p1);
-    embed = std::max(t0, t1) > 0.25 || 0.5 * (p0 + p1) >= 3.5;
+    // small graphs keep their slot streams resident in shared memory (den_shared.cu), which takes the embedded format
+    const int Gw = (group_width == 1 || group_width == 2) ? group_width : 4;
+    const double resident = 3.0 * Kv * 8 * 1.3 + 4.0 * Gw * (2.0 * R_pad + 3.0 * D_pad + 64);
+    const bool by_shape = std::max(t0, t1) > 0.25 || 0.5 * (p0 + p1) >= 3.5;
+    tried_resident = !by_shape && !no_resident && resident <= 240.0 * 1024;   // verified after packing, see below
+    embed = by_shape || tried_resident;
     if (const char *e = getenv("CHAIN_B200_EMBED_CODES")) embed = atoi(e) != 0;
   }
   for (int i = 0; i < kNumViews; i++) vb[i] = ViewBuild();
@@ -593,6 +600,15 @@ int64_t pack_den_blob(const int32_t *ft, const int32_t *fi, const float *fp, con
   int max_sub = 0;
   for (int i = 0; i < kNumViews; i++) max_sub = std::max(max_sub, vb[i].n_sub);
   const long need = 2L * R_pad + 3L * D_pad + max_sub;
+  if (tried_resident) {   // embedded only for the sake of residency: does it really fit (den_shared.cu's launcher test)?
+    size_t slot_bytes = 0;
+    for (int i = 0; i < kNumViews; i++)
+      for (int wv = 0; wv < DEN_NW; wv++) slot_bytes += (size_t)vb[i].warp_info[3 * wv + 1] * 512;
+    if ((size_t)need * 4 * G + 128 + slot_bytes + 16 > (size_t)227 * 1024) {
+      no_resident = true;   // pack again, compact
+      continue;
+    }
+  }
   if (C == 0 || need <= chip_floats || attempt >= 4) break;
   c_cap = std::max(0L, (long)C - ((need - chip_floats + 1) / 2 + 4));
   }
