@@ -30,8 +30,6 @@ struct DenParams {
   float *logp, *grad, *diag;
   float *alpha_ws, *tot_ws;
   int num_groups, use_tma_x, max_sub;
-  int alpha_prefetch;    // a third state row is available: the backward pass fetches alpha rows one frame ahead
-  uint32_t row3_off;     // its byte offset in the CTA's dynamic shared memory
   // records resident in shared memory (small graphs): byte offset of every warp's slot stream of every view inside
   // the CTA's record area (which follows the split-row slots), filled by the launcher from the host blob
   uint32_t rs_off[kNumViews][DEN_NW];

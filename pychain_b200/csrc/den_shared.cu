@@ -576,9 +576,6 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
     // ============================================================ backward
     // P: alpha'(t) (TMA-loaded), Q: beta(t+1).  Both forward buffers are free now.
     float *P = buf0, *Q = buf1;
-    // With room for a THIRD state row (small graphs) the alpha row of frame t-1 is fetched while frame t is processed:
-    // R is the row being filled.  Otherwise the row of frame t is fetched at the top of frame t (latency exposed).
-    float *R = p.alpha_prefetch ? reinterpret_cast<float *>(smem_raw + p.row3_off) : nullptr;
     auto fetch_alpha = [&](float *dst, int f) {
       if (tid == 0) {
         fence_proxy_async();
@@ -591,13 +588,14 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
     for (int i = tid; i < S_pad * G; i += DEN_NT) Q[i] = 0.f;
     if (Lmax > 0) issue_x(Lmax - 1);
     __syncthreads();
-    if (R && Lmax > 0) fetch_alpha(P, Lmax - 1);
     for (int t = Lmax - 1; t >= 0; t--) {
       // utterances that end at t+1 enter here: beta(L) = final/Z + c * sum_k final_k leaky_k / Z
       bool inject = false;
 #pragma unroll
       for (int g = 0; g < G; g++) inject |= (Lg[g] == t + 1);
-      if (!R) fetch_alpha(P, t);
+      // (fetching this row one frame ahead into a third buffer, where one fits, was measured: no gain at cfg5, and
+      //  the larger shared-memory footprint cost the co-resident numerator kernel of cfg3 0.4 ms)
+      fetch_alpha(P, t);
       if (inject) {
         for (int i = tid; i < S; i += DEN_NT) {
           float v[G];
@@ -619,7 +617,6 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       mbar_wait(&mbar[0], ph_a); ph_a ^= 1u;
       __syncthreads();  // P, Q, x_s ready; xraw free
       if (t > 0) issue_x(t - 1);
-      if (R && t > 0) fetch_alpha(R, t - 1);   // R was last read (as beta(t+2)) before the barrier that ended frame t+1
       // bx_c = beta(t+1, dst_c) * x(t, pdf_c) per class, next to beta in the Q row (read by view 4 below)
       for (int k = tid; k < C; k += DEN_NT) {
         float q[G], xv[G];
@@ -700,8 +697,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
             if (b0 + g < p.B) { p.diag[2 * (b0 + g)] = ab[g]; p.diag[2 * (b0 + g) + 1] = gsum[g]; }
         }
       }
-      if (R) { float *tmp = Q; Q = P; P = R; R = tmp; }   // Q <- beta(t); P <- alpha'(t-1) (in flight); R <- free
-      else { float *tmp = P; P = Q; Q = tmp; }             // Q <- beta(t); P <- free
+      float *tmp = P; P = Q; Q = tmp;  // Q <- beta(t); P <- free
       __syncthreads();
     }
     // utterances of length 0 and padded frames t >= Lmax
@@ -802,15 +798,7 @@ int chain_b200_den_forward_backward(const void *blob_host, const void *blob_dev,
   const size_t rec_bytes = resident_record_bytes(blob_host, h, p.rs_off);
   const bool res = h.embed_codes && !h.log_domain && smem + rec_bytes + 16 <= (size_t)227 * 1024 &&
                    !getenv("CHAIN_B200_NO_RESIDENT_RECORDS");
-  size_t smem_launch = smem + (res ? rec_bytes + 16 : 0);
-  // room for a third state row: the backward pass then fetches its alpha rows one frame ahead
-  {
-    const size_t row = (size_t)h.R_pad * G * sizeof(float);
-    const size_t at = (smem_launch + 127) / 128 * 128;
-    p.alpha_prefetch = (!h.log_domain && at + row <= (size_t)227 * 1024 && !getenv("CHAIN_B200_NO_ALPHA_PREFETCH")) ? 1 : 0;
-    p.row3_off = (uint32_t)at;
-    if (p.alpha_prefetch) smem_launch = at + row;
-  }
+  const size_t smem_launch = smem + (res ? rec_bytes + 16 : 0);
   cudaError_t e;
   if (h.log_domain) {  // same blob layout, log semiring (den_shared_log.cu)
     const int st = launch_den_shared_log(h, p, G, l1c, grid, smem, stream);
