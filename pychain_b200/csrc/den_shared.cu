@@ -259,6 +259,21 @@ __device__ __forceinline__ Epi run_pass(const DView &v, uint32_t rec_s /* this w
                                                 bmax, part_s, rp, aux_tab, epi);
 }
 
+// Hint the head of the stream this warp walks NEXT into L1 (no registers): a pass begins by waiting a full L2
+// latency for its first bank, eight times per frame pair; the next pass's first pairs are requested while this warp
+// still sits in the current phase's tail and barrier.  (Streaming loads hit L1 when the line is there.)
+#ifndef CHAIN_B200_PREFETCH_PAIRS
+#define CHAIN_B200_PREFETCH_PAIRS 3
+#endif
+template <bool L1C, bool EMBED>
+__device__ __forceinline__ void prefetch_head(const DView &v, int warp, int lane) {
+  if constexpr (!(L1C && EMBED) && CHAIN_B200_PREFETCH_PAIRS > 0) {
+    const uint4 *sp = reinterpret_cast<const uint4 *>(v.recs + v.warp_info[3 * warp]) + lane;
+#pragma unroll
+    for (int d = 0; d < CHAIN_B200_PREFETCH_PAIRS; d++) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + d * 32));
+  }
+}
+
 // ---- the epilogues of the five passes: what happens to a finished row --------------------------------------
 template <int G> struct EpiClass {   // view 3: class sum -> extension of the state row (shared) + its spill (global)
   uint32_t ext_s; float *ext_g;
@@ -498,6 +513,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         epi_cls = run_pass<G, L1C, EMBED, true, nf1<G>()>(views[3], rec_sa + p.rs_off[3][warp], smem_u32(A), 0u, S - 1, 0, part_sa, nullptr, warp, lane, epi_cls);
         if (p.view[3].n_split) { __syncthreads(); fixup_split<G>(p.view[3], partial, nullptr, epi_cls); }
       }
+      prefetch_head<L1C, EMBED>(views[0], warp, lane);
       __syncthreads();  // x_s complete, xraw free, class sums complete
       if (t < Lmax) issue_x(t);
       EpiAlpha<G> epi_fwd;
@@ -507,6 +523,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       epi_fwd = run_pass<G, L1C, EMBED, false, nf2a<G>()>(views[0], rec_sa + p.rs_off[0][warp], smem_u32(A), smem_u32(x_s), R_pad - 1, D - 1,
                                                           part_sa, nullptr, warp, lane, epi_fwd);
       if (p.view[0].n_split) { __syncthreads(); fixup_split<G>(p.view[0], partial, nullptr, epi_fwd); }
+      prefetch_head<L1C, EMBED>(views[C ? 3 : 0], warp, lane);
 #pragma unroll
       for (int g = 0; g < G; g++) {
         const float ps = warp_sum(epi_fwd.part[g]);
@@ -632,6 +649,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       epi_gam = run_pass<G, L1C, EMBED, false, nf2<G>()>(views[2], rec_sa + p.rs_off[2][warp], smem_u32(P), smem_u32(Q), R_pad - 1, S - 1,
                                                           part_sa, nullptr, warp, lane, epi_gam);
       if (p.view[2].n_split) { __syncthreads(); fixup_split<G>(p.view[2], partial, nullptr, epi_gam); }
+      prefetch_head<L1C, EMBED>(views[C ? 4 : 1], warp, lane);
       __syncthreads();  // gamma rows complete; everybody done reading P; bx complete
 
       // ---- beta' pass, class arcs: rows = source states, one operand (bx_c) per arc; the raw sums wait in P
@@ -639,6 +657,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         EpiStore<G> epi_b2{smem_u32(P)};
         epi_b2 = run_pass<G, L1C, EMBED, true, nf1<G>()>(views[4], rec_sa + p.rs_off[4][warp], smem_u32(Q), 0u, R_pad - 1, 0, part_sa, nullptr, warp, lane, epi_b2);
         if (p.view[4].n_split) { __syncthreads(); fixup_split<G>(p.view[4], partial, nullptr, epi_b2); }
+        prefetch_head<L1C, EMBED>(views[1], warp, lane);
         __syncthreads();
       }
 
@@ -650,6 +669,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
       epi_bwd = run_pass<G, L1C, EMBED, false, nf2<G>()>(views[1], rec_sa + p.rs_off[1][warp], smem_u32(Q), smem_u32(x_s), S - 1, D - 1,
                                                           part_sa, lk, warp, lane, epi_bwd);
       if (p.view[1].n_split) { __syncthreads(); fixup_split<G>(p.view[1], partial, lk, epi_bwd); }
+      prefetch_head<L1C, EMBED>(views[2], warp, lane);
 #pragma unroll
       for (int g = 0; g < G; g++) {
         const float ls = warp_sum(epi_bwd.lpart[g]);
