@@ -83,6 +83,10 @@ template <int G> __host__ __device__ constexpr int nf2() { return G == 4 ? CHAIN
 #define CHAIN_B200_NF2A_G4 CHAIN_B200_NF2_G4
 #endif
 template <int G> __host__ __device__ constexpr int nf2a() { return G == 4 ? CHAIN_B200_NF2A_G4 : kFifoPairs; }  // alpha pass
+#ifndef CHAIN_B200_PREFETCH_AHEAD
+#define CHAIN_B200_PREFETCH_AHEAD 1
+#endif
+constexpr int kPrefetchAhead = CHAIN_B200_PREFETCH_AHEAD;   // banks requested into L1 beyond the two register banks
 #ifndef CHAIN_B200_PAIR_FENCE
 #define CHAIN_B200_PAIR_FENCE 1
 #endif
@@ -222,6 +226,10 @@ __device__ CHAIN_B200_PASS_ATTR Epi sell_pass(const uint4 *__restrict__ sp, cons
 #pragma unroll
     for (int d = 0; d < NF; d++) fb[d] = ldg_stream<L1C>(sp + d * 32);
     sp += NF * 32;
+    if constexpr (kPrefetchAhead > 0 && !L1C) {   // the banks after the next: requested into L1, no registers held
+#pragma unroll
+      for (int d = 0; d < kPrefetchAhead * NF; d++) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + (NF + d) * 32));
+    }
 #pragma unroll
     for (int d = 0; d < NF; d++) process(make_uint2(fa[d].x, fa[d].y), make_uint2(fa[d].z, fa[d].w));
 #pragma unroll
