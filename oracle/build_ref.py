@@ -49,6 +49,7 @@ def build(force=False, verbose=False):
     """Compile the reference extension.  Returns path of the .so, or None when
     the reference tree is absent (GPU box) and no prebuilt .so exists."""
     stage_reference_loss()
+    stage_reference_graph()
     if is_built() and not force:
         if not have_reference():
             return OUT_SO
@@ -97,6 +98,20 @@ REF_LOSS = os.environ.get("PYCHAIN_REFERENCE", "/root/reference") + "/pychain/lo
 STAGED_LOSS = os.path.join(OUT_DIR, "reference_pychain_loss.py")
 
 
+REF_GRAPH = os.environ.get("PYCHAIN_REFERENCE", "/root/reference") + "/pychain/graph.py"
+STAGED_GRAPH = os.path.join(OUT_DIR, "reference_pychain_graph.py")
+
+
+def stage_reference_graph():
+    """Same as stage_reference_loss for the reference's pychain/graph.py: tests/test_fst_golden.py runs it, as is,
+    over the reference-compiled `simplefst` and compares the containers it builds with pychain_b200.graph's."""
+    import shutil
+    if os.path.isfile(REF_GRAPH):
+        os.makedirs(OUT_DIR, exist_ok=True)
+        shutil.copyfile(REF_GRAPH, STAGED_GRAPH)
+    return STAGED_GRAPH if os.path.isfile(STAGED_GRAPH) else None
+
+
 def stage_reference_loss():
     """Stage the reference's UNMODIFIED pychain/loss.py next to the reference .so (oracle/_ref/ is git-ignored and
     travels to the GPU box, where /root/reference does not exist).  tests/test_gpu_dropin.py runs that file, as is,
@@ -106,6 +121,49 @@ def stage_reference_loss():
         os.makedirs(OUT_DIR, exist_ok=True)
         shutil.copyfile(REF_LOSS, STAGED_LOSS)
     return STAGED_LOSS if os.path.isfile(STAGED_LOSS) else None
+
+
+FST_SRC = os.environ.get("PYCHAIN_REFERENCE", "/root/reference") + "/openfst_binding/src/fstext.cc"
+FST_SO = os.path.join(OUT_DIR, "simplefst.so")
+FST_SHIM = os.path.join(HERE, "fst_shim")
+
+
+def build_simplefst(force=False):
+    """Compile the reference's UNMODIFIED openfst_binding/src/fstext.cc (FstToTensor :19-117, SetLeakyProbs
+    :120-171, the `simplefst` module :174-184) into oracle/_ref/simplefst.so.  OpenFst is not in this image, so
+    the include path supplies oracle/fst_shim/fst/fstlib.h, an independent stand-in for the container classes the
+    file touches; the algorithms that run are the reference's.  Returns the .so path or None."""
+    if os.path.isfile(FST_SO) and not force:
+        if not os.path.isfile(FST_SRC):
+            return FST_SO
+        newest = max(os.path.getmtime(FST_SRC), os.path.getmtime(os.path.join(FST_SHIM, "fst", "fstlib.h")))
+        if os.path.getmtime(FST_SO) >= newest:
+            return FST_SO
+    if not os.path.isfile(FST_SRC):
+        return FST_SO if os.path.isfile(FST_SO) else None
+    import torch  # noqa: F401
+    from torch.utils.cpp_extension import include_paths, library_paths
+    os.makedirs(OUT_DIR, exist_ok=True)
+    incs = [f"-I{p}" for p in include_paths()] + [f"-I{sysconfig.get_paths()['include']}", f"-I{FST_SHIM}"]
+    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-w", "-shared", "-DTORCH_EXTENSION_NAME=simplefst",
+           "-DTORCH_API_INCLUDE_EXTENSION_H", "-DNDEBUG"] + incs + [FST_SRC, "-o", FST_SO]
+    for d in library_paths():
+        cmd += [f"-L{d}", f"-Wl,-rpath,{d}"]
+    cmd += ["-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python"]
+    subprocess.check_call(cmd)
+    return FST_SO
+
+
+def load_simplefst():
+    """Import oracle/_ref/simplefst.so under a private module name (the product probes for a real `simplefst`)."""
+    import importlib.util
+    import torch  # noqa: F401
+    if not os.path.isfile(FST_SO):
+        raise FileNotFoundError(FST_SO + " not built (run oracle/build_ref.py where /root/reference exists)")
+    spec = importlib.util.spec_from_file_location("simplefst", FST_SO)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def load():
@@ -125,3 +183,4 @@ def load():
 if __name__ == "__main__":
     so = build(force="--force" in sys.argv, verbose=True)
     print("reference oracle:", so if so else "unavailable (no /root/reference, no prebuilt .so)")
+    print("reference simplefst (over oracle/fst_shim):", build_simplefst(force="--force" in sys.argv))

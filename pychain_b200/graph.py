@@ -123,6 +123,109 @@ class Fst(object):
             fin[s] = w
         return cls(nstates, start or 0, src, dst, pdf, lw, fin)
 
+    # -- binary files: what simplefst.StdVectorFst.read / read_ark / write do (fstext.cc:6-17, 177-179) ------------
+    _MAGIC = 2125659606  # OpenFst's kFstMagicNumber
+
+    @classmethod
+    def read(cls, filename: str, offset: int = 0) -> "Fst":
+        """Read an OpenFst binary "vector" FST over the "standard" (tropical) arc (what `fstcompile` and Kaldi's
+        chain scripts write: den.fst, the numerator FSTs).  Layout: int32 magic | string fsttype | string arctype
+        | int32 version | int32 flags | uint64 properties | int64 start | int64 num_states | int64 num_arcs
+        (string = int32 length + bytes), then per state `float final | int64 narcs | narcs x {int32 ilabel,
+        int32 olabel, float weight, int32 nextstate}`.  Files with embedded symbol tables are refused.
+        `offset` seeks first, as `read_ark` (fstext.cc:7-16) does for an entry of a Kaldi archive."""
+        with open(filename, "rb") as f:
+            f.seek(int(offset))
+            buf = f.read()
+        pos = 0
+
+        def take(dtype, n=1):
+            nonlocal pos
+            a = np.frombuffer(buf, dtype=dtype, count=n, offset=pos)
+            pos += a.nbytes
+            return a
+
+        def take_str():
+            nonlocal pos
+            n = int(take("<i4")[0])
+            if n < 0 or pos + n > len(buf):
+                raise ValueError("Fst.read: {}: corrupt header".format(filename))
+            v = buf[pos:pos + n].decode("ascii", "replace")
+            pos += n
+            return v
+
+        try:
+            if int(take("<i4")[0]) != cls._MAGIC:
+                raise ValueError("Fst.read: {}: not an OpenFst binary file (bad magic number)".format(filename))
+            fsttype, arctype = take_str(), take_str()
+            version, flags = (int(v) for v in take("<i4", 2))
+            take("<u8")  # properties: recomputed from the arcs where needed
+            start, nstates, narcs_total = (int(v) for v in take("<i8", 3))
+            if fsttype != "vector" or arctype != "standard":
+                raise ValueError("Fst.read: {}: fst type {!r} / arc type {!r}; only vector/standard is supported "
+                                 "(convert with fstconvert)".format(filename, fsttype, arctype))
+            if flags & 3:
+                raise ValueError("Fst.read: {}: embedded symbol tables are not supported (strip them with "
+                                 "fstsymbols --clear_isymbols --clear_osymbols)".format(filename))
+            if flags & 4:
+                raise ValueError("Fst.read: {}: aligned files are not supported".format(filename))
+            arc_t = np.dtype([("il", "<i4"), ("ol", "<i4"), ("w", "<f4"), ("ns", "<i4")])
+            fin = np.empty(nstates, dtype=np.float32)
+            counts = np.empty(nstates, dtype=np.int64)
+            chunks = []
+            for s in range(nstates):
+                fin[s] = take("<f4")[0]
+                n = int(take("<i8")[0])
+                if n < 0:
+                    raise ValueError("negative arc count")
+                counts[s] = n
+                chunks.append(take(arc_t, n))
+        except (ValueError, TypeError) as e:
+            if isinstance(e, ValueError) and str(e).startswith("Fst.read"):
+                raise
+            raise ValueError("Fst.read: {}: truncated or corrupt file ({})".format(filename, e))
+        arcs = np.concatenate(chunks) if chunks else np.empty(0, dtype=arc_t)
+        src = np.repeat(np.arange(nstates, dtype=np.int64), counts)
+        return cls(nstates, start, src, arcs["ns"], arcs["il"].astype(np.int64) - 1, -arcs["w"], -fin)
+
+    @classmethod
+    def read_ark(cls, filename: str, offset: int) -> "Fst":
+        """`simplefst.StdVectorFst.read_ark` (fstext.cc:7-16): the FST that starts at byte `offset` of an archive."""
+        return cls.read(filename, offset)
+
+    def write(self, filename: str) -> bool:
+        """Write the OpenFst binary layout `read` parses (olabel = ilabel, properties 0 = unknown)."""
+        S = self._num_states
+        counts = np.bincount(self.src, minlength=S).astype(np.int64)
+        arc_t = np.dtype([("il", "<i4"), ("ol", "<i4"), ("w", "<f4"), ("ns", "<i4")])
+        arcs = np.empty(self.num_arcs, dtype=arc_t)
+        arcs["il"] = arcs["ol"] = self.pdf + 1
+        arcs["w"] = -self.log_weight
+        arcs["ns"] = self.dst
+        ends = np.cumsum(counts)
+        with open(filename, "wb") as f:
+            f.write(np.array([self._MAGIC], "<i4").tobytes())
+            for name in (b"vector", b"standard"):
+                f.write(np.array([len(name)], "<i4").tobytes() + name)
+            f.write(np.array([2, 0], "<i4").tobytes())
+            f.write(np.array([0], "<u8").tobytes())
+            f.write(np.array([self._start, S, self.num_arcs], "<i8").tobytes())
+            fin = (-self.final_log_weight).astype("<f4")
+            for s in range(S):
+                f.write(fin[s:s + 1].tobytes())
+                f.write(counts[s:s + 1].astype("<i8").tobytes())
+                f.write(arcs[ends[s] - counts[s]:ends[s]].tobytes())
+        return True
+
+    # the static spellings `pychain/graph.py` calls on simplefst.StdVectorFst (graph.py:44,48,61)
+    @staticmethod
+    def fst_to_tensor(fst: "Fst", log_domain: bool = False):
+        return list(fst.to_tensors(log_domain))
+
+    @staticmethod
+    def set_leaky_probs(fst: "Fst") -> torch.Tensor:
+        return fst.leaky_probs()
+
     # -- fstext.cc:19-117 restated ---------------------------------------------
     def to_tensors(self, log_domain: bool = False):
         """CSR by source and CSR by destination, as `FstToTensor` emits them.
