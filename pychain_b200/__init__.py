@@ -12,11 +12,14 @@ from .loss import *  # noqa: F401,F403
 
 def install_as_pychain():
     """Make `import pychain`, `import pychain.loss`, `import pychain.graph` and
-    `import pychain_C` resolve to this package (drop-in for existing recipes)."""
+    `import pychain_C` resolve to this package (drop-in for existing recipes); `import simplefst` resolves to
+    the OpenFst-free stand-in unless the reference's real binding is installed."""
     import sys
-    from . import graph, loss, pychain_C
+    from . import graph, loss, pychain_C, simplefst
     me = sys.modules[__name__]
     sys.modules.setdefault("pychain", me)
     sys.modules.setdefault("pychain.loss", loss)
     sys.modules.setdefault("pychain.graph", graph)
     sys.modules.setdefault("pychain_C", pychain_C)
+    if graph.simplefst is None:
+        sys.modules.setdefault("simplefst", simplefst)

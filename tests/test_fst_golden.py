@@ -213,3 +213,33 @@ def test_reference_graph_py_over_reference_simplefst_equals_ours(tmp_path):
     order = torch.tensor([2, 0, 1])
     a.reorder(order), b.reorder(order)
     same_batch(a, b)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_reference_graph_py_over_our_simplefst_stand_in(name):
+    """The other direction: the reference's unmodified pychain/graph.py driven by pychain_b200.simplefst (what a
+    recipe gets after install_as_pychain() on a machine without OpenFst) reproduces the golden tensors."""
+    staged = build_ref.stage_reference_graph()
+    if staged is None:
+        pytest.skip("reference pychain/graph.py not staged")
+    import pychain_b200.simplefst as ours
+    saved = sys.modules.get("simplefst")
+    sys.modules["simplefst"] = ours
+    try:
+        spec = importlib.util.spec_from_file_location("reference_pychain_graph2", staged)
+        rg = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(rg)
+    finally:
+        if saved is None:
+            sys.modules.pop("simplefst", None)
+        else:
+            sys.modules["simplefst"] = saved
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    fst = ours.StdVectorFst.read(os.path.join(GOLDEN, name + ".fst"))
+    for dom, flag in (("prob", False), ("log", True)):
+        g = rg.ChainGraph(fst, log_domain=flag)
+        assert g.num_states == int(z["num_states"]) and g.start_state == int(z["start_state"])
+        for n in TENSOR_NAMES:
+            _same(getattr(g, n).numpy(), z[dom + "_" + n], n)
+        if not flag:
+            np.testing.assert_allclose(g.leaky_probs.numpy(), z["leaky_probs"], rtol=1e-6, atol=1e-12)
