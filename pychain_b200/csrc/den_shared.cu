@@ -356,6 +356,22 @@ __device__ __forceinline__ void fixup_split(const DView &v, const float *__restr
 // L1C: the three record streams fit in the L1 next to this CTA's shared memory, so they are
 // loaded with L1 allocation and hit L1 from the second frame on (small graphs are latency bound);
 // otherwise they are streamed from L2 without polluting L1.
+// The per-frame single-thread duties -- issuing the TMA copy of the next frame of x, issuing the reload of an alpha
+// row, the log-likelihood bookkeeping -- sit at the start of a phase every other warp then waits out at the next
+// barrier.  They are given to three different warps (and the bookkeeping to one lane per utterance) instead of all
+// to thread 0, so no single warp carries the sum of them into every phase.
+#ifndef CHAIN_B200_EARLY_LK
+#define CHAIN_B200_EARLY_LK 1
+#endif
+#ifndef CHAIN_B200_EARLY_TOT
+#define CHAIN_B200_EARLY_TOT 1
+#endif
+#ifndef CHAIN_B200_EARLY_CLS
+#define CHAIN_B200_EARLY_CLS 1
+#endif
+constexpr bool kEarlyLeaky = CHAIN_B200_EARLY_LK != 0, kEarlyTot = CHAIN_B200_EARLY_TOT != 0, kEarlyCls = CHAIN_B200_EARLY_CLS != 0;
+constexpr int kWarpIssueX = DEN_NW - 1, kWarpFetchA = DEN_NW > 1 ? DEN_NW - 2 : 0, kWarpTot = DEN_NW > 2 ? DEN_NW - 3 : 0;
+
 template <int G, bool L1C, bool EMBED>
 __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -433,7 +449,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
     // stage one frame of x: TMA bulk copies into xraw (one per live utterance) ...
     auto issue_x = [&](int f) {
       if (!p.use_tma_x) return;
-      if (tid == 0) {
+      if (tid == kWarpIssueX * 32) {
         fence_proxy_async();
         uint32_t bytes = 0;
 #pragma unroll
@@ -537,8 +553,22 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         const float ps = warp_sum(epi_fwd.part[g]);
         if (lane == 0) red[warp * G + g] = ps;
       }
-      __syncthreads();  // alpha(t) rows + partial sums visible; everybody done reading A
+      // The leaky (and final) probabilities of the rows this thread adds them to come from L2; the first four rows'
+      // worth are requested BEFORE the barrier that ends the alpha pass, so their latency runs under the wait for
+      // the slowest warp instead of after it.
       bool need_z = false;
+#pragma unroll
+      for (int g = 0; g < G; g++) need_z |= (Lg[g] == t);
+      float l[4], f[4];
+      if constexpr (kEarlyLeaky) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = tid + u * DEN_NT;
+          l[u] = (i < S) ? __ldg(lk + i) : 0.f;
+          f[u] = (need_z && i < S) ? __ldg(fin + i) : 0.f;
+        }
+      }
+      __syncthreads();  // alpha(t) rows + partial sums visible; everybody done reading A
       float ct[G], zp[G];
 #pragma unroll
       for (int g = 0; g < G; g++) {
@@ -546,18 +576,17 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         for (int w = 0; w < DEN_NW; w++) s += red[w * G + g];
         ct[g] = c * s; zp[g] = 0.f;   // ct = c * tot(t)
         inv[g] = s > 0.f ? 1.0f / s : 0.f;
-        need_z |= (Lg[g] == t);
       }
       float *awt = aws + (size_t)t * R_pad * G;
-      // alpha'(t) = alpha(t) + c tot(t) leaky; spill.  The leaky (and final) probabilities come from L2: four rows'
-      // worth are requested before the first is used.
+      // alpha'(t) = alpha(t) + c tot(t) leaky; spill
       for (int i0 = tid; i0 < S; i0 += 4 * DEN_NT) {
-        float l[4], f[4];
+        if (!kEarlyLeaky || i0 != tid) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int i = i0 + u * DEN_NT;
-          l[u] = (i < S) ? __ldg(lk + i) : 0.f;
-          f[u] = (need_z && i < S) ? __ldg(fin + i) : 0.f;
+          for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * DEN_NT;
+            l[u] = (i < S) ? __ldg(lk + i) : 0.f;
+            f[u] = (need_z && i < S) ? __ldg(fin + i) : 0.f;
+          }
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -572,16 +601,12 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
           }
         }
       }
-      if (tid == 0) {
-        float tv[G];
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-          float s = 0.f;
-          for (int w = 0; w < DEN_NW; w++) s += red[w * G + g];   // tot(t), same order as above
-          tv[g] = s;
-          if (t < Lg[g]) logp[g] += (double)logf(s);
-        }
-        st_vec<G>(tws + (size_t)t * G, tv);
+      if (warp == kWarpTot && lane < G) {   // one lane per utterance (not thread 0 for all: see kWarpIssueX)
+        const int g = lane;
+        float s = 0.f;
+        for (int w = 0; w < DEN_NW; w++) s += red[w * G + g];   // tot(t), same order as above
+        if (t < Lg[g]) logp[g] += (double)logf(s);
+        tws[(size_t)t * G + g] = s;
       }
       if (need_z) {
         block_sum_vec<G>(zp, red2);
@@ -602,7 +627,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
     // P: alpha'(t) (TMA-loaded), Q: beta(t+1).  Both forward buffers are free now.
     float *P = buf0, *Q = buf1;
     auto fetch_alpha = [&](float *dst, int f) {
-      if (tid == 0) {
+      if (tid == kWarpFetchA * 32) {
         fence_proxy_async();
         mbar_expect_tx(&mbar[0], (uint32_t)R_pad * G * 4u);   // [alpha'(f) | class sums A_c(f)]
         tma_load_1d(dst, aws + (size_t)f * R_pad * G, (uint32_t)R_pad * G * 4u, &mbar[0]);
@@ -613,6 +638,12 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
     for (int i = tid; i < S_pad * G; i += DEN_NT) Q[i] = 0.f;
     if (Lmax > 0) issue_x(Lmax - 1);
     __syncthreads();
+    // tot(t) of the frame about to be processed: spilled by the forward pass, requested one phase before it is
+    // needed (after the beta' pass of the previous frame) so that its L2 latency is not on the frame's critical path
+    float tv[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) tv[g] = 0.f;
+    if (kEarlyTot && Lmax > 0) ld_vec<G>(tws + (size_t)(Lmax - 1) * G, tv);
     for (int t = Lmax - 1; t >= 0; t--) {
       // utterances that end at t+1 enter here: beta(L) = final/Z + c * sum_k final_k leaky_k / Z
       bool inject = false;
@@ -632,21 +663,21 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
           st_vec<G>(Q + (size_t)i * G, v);
         }
       }
-      {
-        float tv[G];
-        ld_vec<G>(tws + (size_t)t * G, tv);
+      if constexpr (!kEarlyTot) ld_vec<G>(tws + (size_t)t * G, tv);
 #pragma unroll
-        for (int g = 0; g < G; g++) inv[g] = (t < Lg[g] && tv[g] > 0.f) ? 1.0f / tv[g] : 0.f;
-      }
+      for (int g = 0; g < G; g++) inv[g] = (t < Lg[g] && tv[g] > 0.f) ? 1.0f / tv[g] : 0.f;   // tv = tot(t)
       transform_x(t, inv);   // x(t,.) / tot(t)
+      int kd0 = 0, kp0 = 0;   // this thread's first class: table entries requested before the barrier
+      if (kEarlyCls && tid < C) { kd0 = __ldg(p.cls_dst + tid); kp0 = __ldg(p.cls_pdf + tid); }
       mbar_wait(&mbar[0], ph_a); ph_a ^= 1u;
       __syncthreads();  // P, Q, x_s ready; xraw free
       if (t > 0) issue_x(t - 1);
       // bx_c = beta(t+1, dst_c) * x(t, pdf_c) per class, next to beta in the Q row (read by view 4 below)
       for (int k = tid; k < C; k += DEN_NT) {
         float q[G], xv[G];
-        ld_vec<G>(Q + (size_t)__ldg(p.cls_dst + k) * G, q);
-        ld_vec<G>(x_s + (size_t)__ldg(p.cls_pdf + k) * G, xv);
+        const int kd = (kEarlyCls && k == tid) ? kd0 : __ldg(p.cls_dst + k), kp = (kEarlyCls && k == tid) ? kp0 : __ldg(p.cls_pdf + k);
+        ld_vec<G>(Q + (size_t)kd * G, q);
+        ld_vec<G>(x_s + (size_t)kp * G, xv);
 #pragma unroll
         for (int g = 0; g < G; g++) q[g] *= xv[g];
         st_vec<G>(Q + (size_t)(S_pad + k) * G, q);
@@ -697,6 +728,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_kernel(const DenParams p
         }
       }
       __syncthreads();  // beta' rows + partials visible; everybody done reading Q and gam_s
+      if (kEarlyTot && t > 0) ld_vec<G>(tws + (size_t)(t - 1) * G, tv);
       float cb[G];
 #pragma unroll
       for (int g = 0; g < G; g++) {

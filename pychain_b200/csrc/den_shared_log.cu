@@ -185,6 +185,8 @@ __device__ __forceinline__ void block_lse_vec(float (&m)[G], float (&s)[G], floa
   __syncthreads();
 }
 
+constexpr int kLogWarpIssueX = DEN_NW - 1, kLogWarpFetchA = DEN_NW > 1 ? DEN_NW - 2 : 0, kLogWarpTot = DEN_NW > 2 ? DEN_NW - 3 : 0;
+
 template <int G, bool L1C, bool EMBED>
 __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
 
     auto issue_x = [&](int f) {
       if (!p.use_tma_x) return;
-      if (tid == 0) {
+      if (tid == kLogWarpIssueX * 32) {   // the single-thread duties are spread over three warps (see den_shared.cu)
         fence_proxy_async();
         uint32_t bytes = 0;
 #pragma unroll
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
         sc[g] = (t <= Lg[g]) ? nsc[g] : 0.f;
         if (t < Lg[g] && nsc[g] > -INFINITY) logp[g] += (double)nsc[g];
       }
-      if (tid == 0) st_vec<G>(tws + (size_t)t * G, sc);
+      if (tid == kLogWarpTot * 32) st_vec<G>(tws + (size_t)t * G, sc);
       finish_utts(Bn, t);
       float *tmp = A; A = Bn; Bn = tmp;
       __syncthreads();
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(DEN_NT, 1) den_shared_log_kernel(const DenPara
       bool inject = false;
 #pragma unroll
       for (int g = 0; g < G; g++) inject |= (Lg[g] == t + 1);
-      if (tid == 0) {
+      if (tid == kLogWarpFetchA * 32) {
         fence_proxy_async();
         mbar_expect_tx(&mbar[0], (uint32_t)S_pad * G * 4u);
         tma_load_1d(P, aws + (size_t)t * S_pad * G, (uint32_t)S_pad * G * 4u, &mbar[0]);
