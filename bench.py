@@ -86,9 +86,20 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             f = [s.strip() for s in line.split(",")]
             if len(f) >= 7:
-                self.samples.append(f)
+                self.samples.append((time.time(), f))
 
-    def stop(self):
+    def wait_first_sample(self, timeout=5.0):
+        """nvidia-smi's start-up (NVML initialisation over every GPU of the box) takes driver locks that stall kernel
+        launches of other processes for up to hundreds of ms: a sampler started right before a short timed region made
+        host-bound configs (cfg3: 40 steps in 36 ms) read 1.3-8 ms per step instead of 0.9.  So it is started before
+        the warm-up and the timed region begins only once it is sampling."""
+        t_end = time.time() + timeout
+        while self.proc and not self.samples and time.time() < t_end and self.proc.poll() is None:
+            time.sleep(0.02)
+
+    def stop(self, t0=None, t1=None):
+        """Clocks over the samples that arrived during [t0, t1] (host times bracketing the timed region; one sampling
+        period of slack on both sides -- a region shorter than the 100 ms period may contain no sample of its own)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         time.sleep(0.15)
@@ -99,7 +110,10 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for f in self.samples:
+        picked = [f for (ts, f) in self.samples if t0 is None or (t0 - 0.12 <= ts <= t1 + 0.16)]
+        if not picked:
+            picked = [f for (_, f) in self.samples]
+        for f in picked:
             try:
                 sm.append(float(f[0]))
                 mx = float(f[1])
@@ -331,6 +345,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the clock sampler starts BEFORE the warm-up (see ClockSampler.wait_first_sample); only the samples taken during
+    # the timed region are reported
+    sampler = ClockSampler(local)
+    if rank == 0 and not a.probe:
+        sampler.start()
     # -------- warm-up (also packs the graph once; not part of a step)
     for _ in range(max(3, a.warmup)):
         r = run_engine(x_dev)
@@ -341,12 +360,12 @@ def main():
     launches0 = engine.launch_count()
 
     # -------- timed: K steps, inputs resident, CUDA events, max over ranks
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.wait_first_sample()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     barrier()
+    t_host0 = time.time()
     e0.record()
     for i in range(a.steps):
         kern_ev[i][0].record()
@@ -355,7 +374,7 @@ def main():
         red = reduce_step(r)
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_host0, time.time()) if rank == 0 else None
     launches = engine.launch_count() - launches0
     ms_total = e0.elapsed_time(e1)
     kern_ms = sum(s.elapsed_time(e) for s, e in kern_ev) / a.steps

@@ -109,10 +109,63 @@ def _cached_upload(tensors, device, shared, names):
     return dev
 
 
+_lengths_cache = OrderedDict()   # (data_ptr, version, numel, dtype, device) -> (the host tensor, its device copy)
+
+
 def _lengths_dev(lengths, device, B):
+    """int64 lengths on the device.  Host lengths (what the reference's recipes pass) are uploaded once per tensor
+    *content* -- the numerator and the denominator call of one loss, and every step that reuses the tensor, share the
+    copy (an in-place edit bumps `_version`; holding the source keeps its address from being recycled)."""
     if lengths.numel() != B:
         raise ValueError("sequence_lengths has {} entries for batch size {}".format(lengths.numel(), B))
-    return lengths.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
+    if lengths.is_cuda or torch.cuda.is_current_stream_capturing():
+        return lengths.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
+    key = (lengths.data_ptr(), lengths._version, lengths.numel(), lengths.dtype, str(device))
+    hit = _lengths_cache.get(key)
+    if hit is not None:
+        _lengths_cache.move_to_end(key)
+        return hit[1]
+    dev = lengths.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
+    _lengths_cache[key] = (lengths, dev)
+    while len(_lengths_cache) > 16:
+        _lengths_cache.popitem(last=False)
+    return dev
+
+
+# Scratch (alpha spill, per-frame totals) is internal to one forward-backward and dead when its kernels finish, so one
+# grow-only buffer per (device, stream) serves every call launched on that stream: kernels of one stream run in order.
+# torch.empty per call costs ~25 us each on this path (blocks that were used on the side stream are recycled through
+# events), which matters when a whole ChainLoss step is 0.8 ms of device time.  CHAIN_B200_CACHE_WS=0 turns it off.
+_ws_cache = {}
+
+
+def _workspace(dev, nbytes, tstream, side):
+    """(uint8 scratch tensor, came-from-cache)."""
+    nbytes = max(int(nbytes), 1)
+    if os.environ.get("CHAIN_B200_CACHE_WS", "1") == "0" or torch.cuda.is_current_stream_capturing():
+        return torch.empty(nbytes, dtype=torch.uint8, device=dev), False
+    key = (dev.index or 0, tstream.cuda_stream)
+    t = _ws_cache.get(key)
+    if t is None or t.numel() < nbytes:
+        if t is not None and side:
+            t.record_stream(tstream)   # the block goes back to the allocator: kernels of `tstream` may still use it
+        t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _ws_cache[key] = t
+    return t, True
+
+
+def release_workspaces():
+    """Drop the cached scratch buffers (they are as large as the largest batch seen: B*(T+1)*(S+classes)*4 bytes)."""
+    for (idx, _), t in list(_ws_cache.items()):
+        with torch.cuda.device(idx):
+            torch.cuda.synchronize()
+    _ws_cache.clear()
+
+
+def _small_outputs(B, dev):
+    """objf, ok, diag[8] and logp[B] carved from ONE allocation: [0] objf | [1] ok (int32) | [8:16] diag | [16:] logp."""
+    small = torch.empty(16 + B, dtype=torch.float32, device=dev)
+    return small, small[0], small[1:2].view(torch.int32), small[8:16], small[16:16 + B]
 
 
 def _launch_stream(dev, stream):
@@ -141,14 +194,13 @@ def _run_generic(log_domain, graph_tensors, x, lengths, num_states, leaky_coeffi
     dev = x.device
     g = _cached_upload(list(graph_tensors), dev, shared, names)
     ldev = _lengths_dev(lengths, dev, B)
-    objf = torch.empty((), dtype=torch.float32, device=dev)
-    logp = torch.empty(B, dtype=torch.float32, device=dev) if want_logp else None
+    small, objf, ok, diag, logp = _small_outputs(B, dev)
+    if not want_logp:
+        logp = None
     grad = torch.empty_like(x)
-    ok = torch.empty(1, dtype=torch.int32, device=dev)
-    diag = torch.empty(8, dtype=torch.float32, device=dev)
     ws_bytes = lib.chain_b200_workspace_bytes(B, T, D, S, K, flags)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     tstream, cstream = _launch_stream(dev, stream)
+    ws, ws_cached = _workspace(dev, ws_bytes, tstream, stream is not None)
     if log_domain:
         st = lib.chain_b200_forward_backward_log_domain(
             *[_ptr(t) for t in g], _ptr(x), _ptr(ldev), B, T, D, S, K, flags, float(grad_scale),
@@ -161,7 +213,7 @@ def _run_generic(log_domain, graph_tensors, x, lengths, num_states, leaky_coeffi
         _cabi.check(st, "chain_b200_forward_backward")
     _launches += lib.chain_b200_last_launch_count()
     if stream is not None:  # every buffer of the current stream's pool that the side-stream kernels touch
-        _record_side_stream(tstream, [ws, x, ldev, objf, logp, grad, ok, diag] + list(g))
+        _record_side_stream(tstream, [None if ws_cached else ws, x, ldev, small, grad] + list(g))
     return Result(objf, logp, grad, ok, diag)
 
 
@@ -229,21 +281,18 @@ def _run_den_shared(prep, x, lengths, leaky_coefficient, flags, stream=None, gra
         raise ValueError("graph was prepared for {} pdfs, input has {}".format(prep.D, D))
     dev = x.device
     ldev = _lengths_dev(lengths, dev, B)
-    objf = torch.empty((), dtype=torch.float32, device=dev)
-    logp = torch.empty(B, dtype=torch.float32, device=dev)
+    small, objf, ok, diag, logp = _small_outputs(B, dev)
     grad = torch.empty_like(x)
-    ok = torch.empty(1, dtype=torch.int32, device=dev)
-    diag = torch.empty(8, dtype=torch.float32, device=dev)
     ws_bytes = lib.chain_b200_den_workspace_bytes(_ptr(prep.blob_host), B, T)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     tstream, cstream = _launch_stream(dev, stream)
+    ws, ws_cached = _workspace(dev, ws_bytes, tstream, stream is not None)
     st = lib.chain_b200_den_forward_backward(
         _ptr(prep.blob_host), _ptr(prep.blob_dev), prep.copies, _ptr(x), _ptr(ldev), B, T, D, float(leaky_coefficient), flags,
         float(grad_scale), _ptr(objf), _ptr(logp), _ptr(grad), _ptr(ok), _ptr(diag), _ptr(ws), ws_bytes, dev.index or 0, cstream)
     _cabi.check(st, "chain_b200_den_forward_backward")
     _launches += lib.chain_b200_last_launch_count()
     if stream is not None:
-        _record_side_stream(tstream, [ws, x, ldev, objf, logp, grad, ok, diag, prep.blob_dev])
+        _record_side_stream(tstream, [None if ws_cached else ws, x, ldev, small, grad, prep.blob_dev])
     return Result(objf, logp, grad, ok, diag)
 
 

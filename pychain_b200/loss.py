@@ -137,7 +137,13 @@ class _ChainLossFunction(torch.autograd.Function):
         host_lengths = _check_lengths(input, input_lengths)
         lengths = input_lengths.detach()
         scale = 1.0 / float(host_lengths.sum()) if avg else 1.0
-        den_graphs = ChainGraphBatch(den_graph, B)  # stride-0 views: O(1), not a B-fold copy (loss.py:99)
+        # stride-0 views: O(1), not a B-fold copy (loss.py:99); built once per batch size and kept with the graph
+        cache = den_graph.__dict__.setdefault("_batch_cache", {})
+        den_graphs = cache.get(B)
+        if den_graphs is None:
+            if len(cache) > 8:
+                cache.clear()
+            den_graphs = cache[B] = ChainGraphBatch(den_graph, B)
         gd = tuple(getattr(den_graphs, n) for n in engine._GRAPH_NAMES_PROB)
         gn = tuple(getattr(num_graphs, n) for n in (engine._GRAPH_NAMES_LOG if num_graphs.log_domain
                                                     else engine._GRAPH_NAMES_PROB))
