@@ -413,3 +413,20 @@ def test_materialised_batch_detection_host_side():
     assert engine._shared_rows(tuple(getattr(mat, n) for n in engine._GRAPH_NAMES_PROB), 6) == (None, None)
     nb = synth.make_num_batch(4, 30, 8, seed=1, min_phones=2, max_phones=4)
     assert engine._shared_rows(tuple(getattr(nb, n) for n in engine._GRAPH_NAMES_LOG), 4) == (None, None)
+
+
+def test_headline_kernel_stream_banks_do_not_wait_for_younger_loads():
+    """ptxas signals every record-stream load of a SELL pass on one scoreboard; if it schedules a register bank's
+    first consumer AFTER the other bank's refill, every loop iteration waits a full L2 latency (measured: cfg4 5.3 ->
+    5.6-6.1 ms).  Source semantics cannot express it, so the built SASS of the cfg4 instantiation is checked
+    (tools/sass_scoreboards.py decodes the control words; profiles/r2_variants.md has the story)."""
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    tool = os.path.join(ROOT, "tools", "sass_scoreboards.py")
+    out = subprocess.run([sys.executable, tool, _cabi.LIB_PATH, "den_shared_kernelILi4ELb0ELb1E"],
+                         capture_output=True, text=True, timeout=300).stdout
+    assert "den_shared_kernelILi4ELb0ELb1E" in out, out[-500:]
+    assert out.strip().splitlines()[-1] == "bad bank pairs: 0", out[-2000:]
