@@ -430,3 +430,64 @@ def test_headline_kernel_stream_banks_do_not_wait_for_younger_loads():
                          capture_output=True, text=True, timeout=300).stdout
     assert "den_shared_kernelILi4ELb0ELb1E" in out, out[-500:]
     assert out.strip().splitlines()[-1] == "bad bank pairs: 0", out[-2000:]
+
+
+def _edge_graphs():
+    """Hand-made denominator graphs at the corners of the packer: (name, Fst, D)."""
+    out = []
+    # one state: a self loop and a final weight
+    out.append(("one_state", Fst(1, 0, [0], [0], [0], [np.log(0.5)], [np.log(0.5)]), 1))
+    # a left-to-right chain with self loops: every slice is one arc pair or less (thin slices)
+    S = 70
+    src = list(range(S)) + list(range(S - 1))
+    dst = list(range(S)) + list(range(1, S))
+    pdf = [i % 7 for i in range(S)] + [(3 * i) % 7 for i in range(S - 1)]
+    fin = np.full(S, -np.inf, np.float32); fin[-1] = np.log(0.5)
+    out.append(("chain", Fst(S, 0, src, dst, pdf, np.full(len(src), np.log(0.5), np.float32), fin), 7))
+    # a star: 100 sources all enter state 0 on the same pdf (ONE class of 100 arcs: longer than a slice is wide),
+    # state 0 fans back out on distinct pdfs
+    S = 101
+    src = list(range(1, S)) + [0] * (S - 1) + [0]
+    dst = [0] * (S - 1) + list(range(1, S)) + [0]
+    pdf = [2] * (S - 1) + [i % 5 for i in range(S - 1)] + [4]
+    w = np.log(np.r_[np.full(S - 1, 0.9), np.full(S - 1, 0.009), 0.05]).astype(np.float32)
+    fin = np.full(S, np.log(0.1), np.float32)
+    out.append(("star", Fst(S, 0, src, dst, pdf, w, fin), 5))
+    # a single pdf: every destination is one class; a few states have no entering arc but the start
+    rng = np.random.default_rng(4)
+    S, K = 40, 300
+    src = np.r_[np.arange(S), rng.integers(0, S, K - S)]
+    dst = np.r_[(np.arange(S) + 1) % S, rng.integers(0, S // 2, K - S)]
+    out.append(("one_pdf", Fst(S, 0, src, dst, np.zeros(K, int), np.full(K, np.log(0.1), np.float32),
+                                np.full(S, np.log(0.2), np.float32)), 1))
+    return out
+
+
+@pytest.mark.parametrize("embed", [0, 1])
+@pytest.mark.parametrize("name", ["one_state", "chain", "star", "one_pdf"])
+def test_den_packer_corner_graphs(name, embed, monkeypatch):
+    """Corner graphs through the packer: every arc is packed exactly once (as a two-operand record or as a class
+    member), and the factorised recursion run from the decoded blob reproduces the oracle."""
+    from oracle import chain_oracle as co
+    fst, D = next((f, d) for n, f, d in _edge_graphs() if n == name)
+    g = ChainGraph(fst, initial_mode="leaky", final_mode="fst")
+    gb = ChainGraphBatch(g, 1)
+    gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_PROB)
+    monkeypatch.setenv("CHAIN_B200_MIN_CLASS", "2")
+    monkeypatch.setenv("CHAIN_B200_EMBED_CODES", str(embed))
+    engine._prepared_cache.clear()
+    b = _parse_blob(engine.prepare_den_graph(gt, g.num_states, D, "cpu").blob_host)
+    engine._prepared_cache.clear()
+    n_cls = len(_decode_view(b["views"][3], 16))
+    assert n_cls == len(_decode_view(b["views"][4], 16))
+    assert len(_decode_view(b["views"][1], 16)) + n_cls == g.num_transitions
+    assert len(_decode_view(b["views"][0], 16)) == len(_decode_view(b["views"][2], 16)) == g.num_transitions - n_cls + b["C"]
+    if name in ("star", "one_pdf"):
+        assert b["C"] > 0
+    T = 6
+    x, lengths = synth.make_inputs(1, T, D, seed=21)
+    ex = x.clamp(-30, 30).exp()
+    o_c, _, g_c, _, _ = co.den_c(gb, ex, lengths, 1e-5)
+    logp, grad = _blob_forward_backward(b, ex[0].double().numpy(), 1e-5)
+    assert abs(logp - o_c) < 2e-6 * abs(o_c) + 5e-6
+    assert np.abs(grad - g_c[0].numpy()).max() < 5e-6
