@@ -491,3 +491,36 @@ def test_den_packer_corner_graphs(name, embed, monkeypatch):
     logp, grad = _blob_forward_backward(b, ex[0].double().numpy(), 1e-5)
     assert abs(logp - o_c) < 2e-6 * abs(o_c) + 5e-6
     assert np.abs(grad - g_c[0].numpy()).max() < 5e-6
+
+
+@pytest.mark.parametrize("S,log_domain,ok", [(65535, False, True), (65536, False, False), (32767, True, True), (32768, True, False)])
+def test_den_packer_index_limits_at_the_boundary(S, log_domain, ok):
+    """16-bit state indices in the packed records (15-bit in the log domain, whose index word carries the slice flag):
+    the largest graph that fits packs, one state more is CHAIN_B200_ERR_UNSUPPORTED (the engine then takes the
+    general kernel) -- never a silently wrapped index."""
+    lib = _cabi.lib()
+    src = torch.arange(S, dtype=torch.int32)
+    dst = (src + 1) % S
+    ft = torch.stack([src, dst, src % 8], 1).contiguous()          # a ring: arc s -> s+1, pdf s mod 8
+    fi = torch.stack([src, src + 1], 1).contiguous()
+    order = torch.argsort(dst.long(), stable=True)
+    bt, bi = ft[order].contiguous(), fi.clone()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    flags = _cabi.LOG_DOMAIN if log_domain else 0
+    got = lib.chain_b200_den_prepare_bytes(p(ft), p(fi), p(bt), p(bi), S, S, 8, flags)
+    if not ok:
+        assert got == _cabi.ERR_UNSUPPORTED
+        return
+    assert got > 0
+    if not log_domain:      # the largest state index survives the packing: decode the blob of the alpha view
+        g = ChainGraph(Fst(S, 0, src.numpy(), dst.numpy(), (src % 8).numpy(), np.full(S, np.log(0.5), np.float32),
+                           np.full(S, np.log(0.5), np.float32)))
+        gb = ChainGraphBatch(g, 1)
+        gt = tuple(getattr(gb, n) for n in engine._GRAPH_NAMES_PROB)
+        engine._prepared_cache.clear()
+        try:
+            b = _parse_blob(engine.prepare_den_graph(gt, S, 8, "cpu").blob_host)
+        finally:
+            engine._prepared_cache.clear()
+        rows = _decode_view(b["views"][0], 16)
+        assert len(rows) == S and (0, S - 1, (S - 1) % 8) in {(r, a, bb) for r, a, bb, _ in rows}
